@@ -1,0 +1,352 @@
+"""CPU/GPU-agnostic ORACLE for the DiffSpectra sampling hot path.  TEST INFRASTRUCTURE ONLY.
+
+A from-scratch, dense (padded [B,N,...] / [B,N,N,...]) functional restatement in plain PyTorch of
+the reference algorithm, operating directly on a reference-compatible ``state_dict``.  Nothing
+here is imported by the product package ``diffspectra_b200``; only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs use it,
+and only as the checker / the timed CPU baseline.
+
+Parity pin: the reference ships no tests or golden vectors, so this restatement is
+pinned against outputs of the UNMODIFIED reference modules run in the build container
+(oracle/gen_golden.py -> tests/golden/*.pt; tests/test_oracle_vs_golden.py), and, when
+/root/reference is present, directly against the reference (tests/test_oracle_vs_reference.py).
+
+Reference lines followed (relative to /root/reference):
+  denoiser       models/dmt.py:306-413 (DMT.forward), :122-174 (EquivariantMixBlock), :37-60 (MultiCondEquiUpdate)
+  attention      models/layers.py:131-186 (TransMixLayer) + PyG MessagePassing/softmax semantics
+  RBF            models/layers.py:291-295, 328-334 ; CoorsNorm :337-347 ; sinusoidal emb :283-288
+  masks / noise  models/utils.py:38-45, 67-106, 118-144
+  SpecFormer     models/specformer.py:77-120, 167-200, 279-309, 345-425, 457-470
+  sampler        sampling.py:565-631 ; post_process sampling.py:53-97 ; inverse scaler utils.py:71-105
+  schedule       diffusion/noise_schedule.py:40-53, 70-91
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------- small helpers
+def _lin(sd, name, x, bias=True):
+    w = sd[name + '.weight']
+    b = sd.get(name + '.bias') if bias else None
+    return F.linear(x, w, b)
+
+
+def _ln(x, eps=1e-6):
+    # LayerNorm without affine (models/dmt.py:86-97, :28)
+    return F.layer_norm(x, (x.shape[-1],), None, None, eps)
+
+
+def _mod(x, shift, scale):
+    # models/dmt.py:13-14
+    return x * (1 + scale) + shift
+
+
+def _cond_rbf(sd, prefix, r, temb):
+    """CondGaussianLayer.forward (models/layers.py:328-334) + gaussian (:291-295).
+    r: [..., 1] squared distance, temb broadcastable [..., 1024] -> [..., 64]."""
+    ss = F.linear(F.silu(temb), sd[prefix + '.time_mlp.1.weight'], sd[prefix + '.time_mlp.1.bias'])
+    scale, shift = ss[..., 0:1], ss[..., 1:2]
+    x = r * (scale + 1) + shift
+    mean = sd[prefix + '.means.weight'].reshape(-1)
+    std = sd[prefix + '.stds.weight'].reshape(-1).abs() + 1e-5
+    a = (2 * 3.14159) ** 0.5
+    g = torch.exp(-0.5 * (((x - mean) / std) ** 2)) / (a * std)
+    return torch.cat([x, g], dim=-1)
+
+
+# ----------------------------------------------------------------------------- SpecFormer
+SPEC_LEN = (701, 3501, 3501)
+
+
+def _used_types(version):
+    return {'uv': [0], 'ir': [1], 'raman': [2], 'allspectra': [0, 1, 2]}[version]
+
+
+def specformer_forward(sd, spectra, version, patch_len=(20, 50, 50), stride=(10, 25, 25),
+                       n_layers=3, n_heads=16, prefix='cond_encoder.'):
+    """spectra: list of [B, L] tensors in used-type order. Returns [B, 256] (before cond_lin)."""
+    used = _used_types(version)
+    toks = []
+    for slot, (ti, spec) in enumerate(zip(used, spectra)):
+        p = spec.unfold(-1, patch_len[ti], stride[ti])                           # [B, P, patch_len]
+        z = F.linear(p, sd[prefix + 'backbone.W_P.%d.weight' % slot], sd[prefix + 'backbone.W_P.%d.bias' % slot])
+        if version == 'allspectra':
+            wpos = sd[prefix + 'backbone.W_pos_' + ('uv', 'ir', 'raman')[ti]]
+        else:
+            wpos = sd[prefix + 'backbone.W_pos']
+        toks.append(z + wpos)
+    z = torch.cat(toks, dim=1)                                                    # [B, Q, 128]
+    B, Q, D = z.shape
+    dk = D // n_heads
+    scores = None
+    for l in range(n_layers):
+        lp = prefix + 'backbone.encoder.layers.%d.' % l
+        q = _lin(sd, lp + 'self_attn.W_Q', z).view(B, Q, n_heads, dk).transpose(1, 2)
+        k = _lin(sd, lp + 'self_attn.W_K', z).view(B, Q, n_heads, dk).permute(0, 2, 3, 1)
+        v = _lin(sd, lp + 'self_attn.W_V', z).view(B, Q, n_heads, dk).transpose(1, 2)
+        s = torch.matmul(q, k) * sd[lp + 'self_attn.sdp_attn.scale']
+        if scores is not None:
+            s = s + scores                                                        # residual attention (specformer.py:401-404)
+        scores = s
+        a = F.softmax(s, dim=-1)
+        o = torch.matmul(a, v).transpose(1, 2).contiguous().view(B, Q, D)
+        o = _lin(sd, lp + 'self_attn.to_out.0', o)
+        z = z + o
+        z = _bn_eval(sd, lp + 'norm_attn.1', z)
+        f = _lin(sd, lp + 'ff.3', F.gelu(_lin(sd, lp + 'ff.0', z)))
+        z = z + f
+        z = _bn_eval(sd, lp + 'norm_ffn.1', z)
+    z = z.reshape(B, Q * D)
+    z = _lin(sd, prefix + 'head.linear', z)
+    z = F.layer_norm(z, (z.shape[-1],), sd[prefix + 'out_norm.weight'], sd[prefix + 'out_norm.bias'], 1e-5)
+    return z
+
+
+def _bn_eval(sd, name, x):
+    # BatchNorm1d over the channel (last) dim in eval mode (specformer.py:249-251 wraps it in Transpose)
+    rm, rv = sd[name + '.running_mean'], sd[name + '.running_var']
+    return (x - rm) / torch.sqrt(rv + 1e-5) * sd[name + '.weight'] + sd[name + '.bias']
+
+
+def context_embedding(sd, context, version):
+    """cond_lin(SpecFormer(context)) -> [B, 1024] (models/dmt.py:348-350).
+    context: Tensor [B,1,L] (single spectrum) or list of three [B,1,L]."""
+    if isinstance(context, (list, tuple)):
+        spectra = [c.reshape(c.shape[0], -1) for c in context]
+    else:
+        spectra = [context.reshape(context.shape[0], -1)]
+    z = specformer_forward(sd, spectra, version)
+    return _lin(sd, 'cond_lin', z)
+
+
+# ----------------------------------------------------------------------------- DMT denoiser
+def time_embedding(sd, noise_level):
+    # LearnedSinusodialposEmb (layers.py:283-288) + time_mlp (dmt.py:249-257)
+    x = noise_level.unsqueeze(-1)
+    freqs = x * sd['time_mlp.0.weights'].unsqueeze(0) * 2 * math.pi
+    f = torch.cat((x, freqs.sin(), freqs.cos()), dim=-1)
+    return _lin(sd, 'time_mlp.3', F.gelu(_lin(sd, 'time_mlp.1', f)))
+
+
+def dmt_forward(sd, xh, node_mask, edge_mask, edge_x, noise_level, cond_x=None, cond_edge_x=None,
+                ctx_emb=None, n_layers=8, n_heads=16, n_extra=2, cutoff=2.0, edge_th=0.0,
+                return_intermediates=False):
+    """Dense restatement of DMT.forward.  ctx_emb = context_embedding(...) [B,1024].
+    Returns ([B,N,9], [B,N,N,2])."""
+    B, N, _ = xh.shape
+    dt = xh.dtype
+    A = edge_mask.reshape(B, N, N).to(dt)                       # A[b,r,c]
+    nm = node_mask.reshape(B, N, 1).to(dt)
+    pos = xh[:, :, 0:3].clone()
+    h = xh[:, :, 3:]
+    if cond_x is None:
+        cond_x = torch.zeros_like(xh)
+        cond_edge_x = torch.zeros_like(edge_x)
+        adj2d = torch.ones(B, N, N, dtype=dt, device=xh.device)
+    else:
+        adj2d = (cond_edge_x[..., 0] >= edge_th).to(dt)
+    cond_pos = cond_x[:, :, 0:3]
+    h = torch.cat([h, cond_x[:, :, 3:]], dim=-1)
+
+    temb = time_embedding(sd, noise_level) + ctx_emb             # [B,1024]
+    temb_e = temb[:, None, None, :]                              # broadcast over (r,c)
+    s_act = F.silu(temb)
+
+    d = cond_pos[:, :, None, :] - cond_pos[:, None, :, :]        # [B,r,c,3]
+    r0 = (d ** 2).sum(-1, keepdim=True)
+    adjsp = (r0[..., 0] <= cutoff).to(dt)
+    if float((r0[..., 0] * A).sum()) == 0:                       # batch-global shortcut (dmt.py:364)
+        d0 = r0.repeat(1, 1, 1, 64)
+    else:
+        d0 = _cond_rbf(sd, 'dist_layer', r0, temb_e)
+    e = _lin(sd, 'edge_emb', torch.cat([edge_x, cond_edge_x, d0], dim=-1))      # [B,N,N,64]
+    h = _lin(sd, 'node_emb', h)                                                  # [B,N,256]
+
+    H, SH, SC, C = n_heads, n_heads - n_extra, (n_heads * 16) // (n_heads - n_extra), 16
+    neg = -1e10
+    atom_hids, edge_hids = [h], [e]
+    inter = {}
+    for l in range(n_layers):
+        bp = 'e_block_%d.' % l
+        h_in, e_in = h, e
+        nsm = F.linear(s_act, sd[bp + 'node_time_mlp.1.weight'], sd[bp + 'node_time_mlp.1.bias'])
+        esm = F.linear(s_act, sd[bp + 'edge_time_mlp.1.weight'], sd[bp + 'edge_time_mlp.1.bias'])
+        nsh1, nsc1, ng1, nsh2, nsc2, ng2 = [t[:, None, :] for t in nsm.chunk(6, dim=1)]
+        esh1, esc1, eg1, esh2, esc2, eg2 = [t[:, None, None, :] for t in esm.chunk(6, dim=1)]
+
+        diff = pos[:, :, None, :] - pos[:, None, :, :]                          # x_r - x_c
+        r2 = (diff ** 2).sum(-1, keepdim=True)
+        dist = _cond_rbf(sd, bp + 'dist_layer', r2, temb_e)                     # [B,N,N,64]
+        ea = _lin(sd, bp + 'edge_emb', torch.cat([dist, e], dim=-1))
+        hh = _mod(_ln(h), nsh1, nsc1)
+        ea = _mod(_ln(ea), esh1, esc1)
+
+        # TransMixLayer (layers.py:131-186): target = c (edge_index[1]), source = r (edge_index[0])
+        ap = bp + 'attn_mpnn.'
+        q = _lin(sd, ap + 'lin_query', hh).view(B, N, SH, SC)
+        k = _lin(sd, ap + 'lin_key', hh).view(B, N, SH, SC)
+        v = _lin(sd, ap + 'lin_value', hh).view(B, N, H, C)
+        e0 = torch.tanh(F.linear(ea, sd[ap + 'lin_edge0.weight'])).view(B, N, N, SH, SC)
+        e1 = torch.tanh(F.linear(ea, sd[ap + 'lin_edge1.weight'])).view(B, N, N, H, C)
+        # alpha[b,r,c,h] = sum_d q[c] k[r] e0[r,c] / sqrt(16)
+        alpha = torch.einsum('bchd,brhd,brchd->brch', q, k, e0) / math.sqrt(C)
+        x0 = torch.where(adj2d == 0, torch.full_like(adj2d, neg), adj2d)
+        x1 = torch.where(adjsp == 0, torch.full_like(adjsp, neg), adjsp)
+        logits = torch.cat([x0[..., None], x1[..., None], alpha], dim=-1)       # [B,r,c,16]
+        Am = A[..., None]
+        lmask = torch.where(Am > 0, logits, torch.full_like(logits, float('-inf')))
+        mx = lmask.max(dim=1, keepdim=True).values
+        mx = torch.where(torch.isfinite(mx), mx, torch.zeros_like(mx))
+        ex = torch.exp(lmask - mx) * Am                                        # exp(-inf)=0 on non-edges
+        att = ex / (ex.sum(dim=1, keepdim=True) + 1e-16)
+        hn = torch.einsum('brch,brhd,brchd->bchd', att, v, e1).reshape(B, N, H * C)
+
+        he = _lin(sd, bp + 'node2edge_lin', hn[:, :, None, :] + hn[:, None, :, :])
+        h1 = _mod(_ln(h_in + ng1 * hn), nsh2, nsc2) * nm
+        ff = _lin(sd, bp + 'ff_linear2', F.silu(_lin(sd, bp + 'ff_linear1', h1)))
+        h = (h1 + ng2 * ff) * nm
+        e1_ = _mod(_ln(e_in + eg1 * he), esh2, esc2)
+        ffe = _lin(sd, bp + 'ff_linear4', F.silu(_lin(sd, bp + 'ff_linear3', e1_)))
+        e = e1_ + eg2 * ffe
+
+        # MultiCondEquiUpdate (dmt.py:37-60)
+        up = bp + 'equi_update.'
+        tsm = F.linear(s_act, sd[up + 'time_mlp.1.weight'], sd[up + 'time_mlp.1.bias'])
+        csh, csc = [t[:, None, None, :] for t in tsm.chunk(2, dim=1)]
+        hr = h[:, :, None, :].expand(B, N, N, h.shape[-1])
+        hc = h[:, None, :, :].expand(B, N, N, h.shape[-1])
+        inp = torch.cat([hr, hc, e, dist], dim=-1)
+        inv = _mod(_ln(_lin(sd, up + 'input_lin', inp)), csh, csc)
+        inv = F.linear(F.silu(_lin(sd, up + 'coord_mlp.0', inv)), sd[up + 'coord_mlp.2.weight'])
+        inv = torch.tanh(inv)                                                     # [B,r,c,3]
+        adjs = torch.stack([torch.ones_like(adj2d), adj2d, adjsp], dim=-1)
+        w = (inv * adjs).mean(-1, keepdim=True)
+        nrm = diff.norm(dim=-1, keepdim=True).clamp(min=1e-8)
+        cd = diff / nrm * sd[up + 'coord_norm.scale']
+        pos = pos + (cd * w * A[..., None]).sum(dim=2)
+        # CoM removal (dmt.py:385-386, models/utils.py:38-45)
+        nn_ = nm.sum(1, keepdim=True)
+        pos = pos - pos.sum(dim=1, keepdim=True) / nn_ * nm
+        atom_hids.append(_lin(sd, 'node_%d' % l, h))
+        edge_hids.append(_lin(sd, 'edge_%d' % l, e))
+        if return_intermediates:
+            inter['h_%d' % l], inter['e_%d' % l], inter['pos_%d' % l] = h, e * Am, pos
+
+    ah = torch.cat(atom_hids, dim=-1)
+    eh = torch.cat(edge_hids, dim=-1)
+
+    def mlp3(name, x):
+        x = F.silu(_lin(sd, name + '.0', x))
+        x = F.silu(_lin(sd, name + '.2', x))
+        return _lin(sd, name + '.4', x)
+
+    atom_pred = mlp3('node_pred_mlp', ah) * nm
+    edge_pred = torch.cat([mlp3('edge_exist_mlp', eh), mlp3('edge_type_mlp', eh)], dim=-1) * A[..., None]
+    edge_final = 0.5 * (edge_pred + edge_pred.permute(0, 2, 1, 3))
+    pos = pos * nm
+    if bool(torch.isnan(pos).any()):
+        pos = torch.zeros_like(pos)
+    nn_ = nm.sum(1, keepdim=True)
+    pos = pos - pos.sum(dim=1, keepdim=True) / nn_ * nm
+    out = torch.cat([pos, atom_pred], dim=2)
+    if return_intermediates:
+        return out, edge_final, inter
+    return out, edge_final
+
+
+# ----------------------------------------------------------------------------- schedule + sampler
+COSINE_S = 0.008
+COSINE_T = 0.9946
+
+
+def cosine_marginal_prob(t):
+    """NoiseScheduleVP('cosine').marginal_prob (noise_schedule.py:40-53, 70-91); t: 0-dim tensor."""
+    log_alpha_0 = math.log(math.cos(COSINE_S / (1. + COSINE_S) * math.pi / 2.))
+    log_alpha = torch.log(torch.cos((t + COSINE_S) / (1. + COSINE_S) * math.pi / 2.)) - log_alpha_0
+    return torch.exp(log_alpha), torch.sqrt(1. - torch.exp(2. * log_alpha))
+
+
+def schedule_table(steps, eps=1e-3, device='cpu', dtype=torch.float32):
+    """[steps,4] = (c_x, c_pred, sigma, noise_level) with the op order of sampling.py:571-584."""
+    t_array = torch.linspace(COSINE_T, eps, steps, device=device, dtype=dtype)
+    s_array = torch.cat([t_array[1:], torch.zeros(1, device=device, dtype=dtype)])
+    rows = []
+    for i in range(steps):
+        alpha_t, sigma_t = cosine_marginal_prob(t_array[i])
+        alpha_s, sigma_s = cosine_marginal_prob(s_array[i])
+        a_ts = alpha_t / alpha_s
+        s2_ts = sigma_t ** 2 - a_ts ** 2 * sigma_s ** 2
+        sigma = torch.sqrt(s2_ts) * sigma_s / sigma_t
+        c_x = a_ts * sigma_s ** 2 / sigma_t ** 2
+        c_pred = alpha_s * s2_ts / sigma_t ** 2
+        nl = torch.log(alpha_t ** 2 / sigma_t ** 2)
+        rows.append(torch.stack([c_x, c_pred, sigma, nl]))
+    return torch.stack(rows)
+
+
+def remove_mean_with_mask(x, node_mask):
+    n = node_mask.sum(1, keepdim=True)
+    return x - x.sum(dim=1, keepdim=True) / n * node_mask
+
+
+def node_noise_from_raw(raw_pos, raw_h, node_mask):
+    """models/utils.py:67-97 with the randn draws supplied: raw_pos [B,N,3], raw_h [B,N,6]."""
+    zx = remove_mean_with_mask(raw_pos * node_mask, node_mask)
+    return torch.cat([zx, raw_h * node_mask], dim=2)
+
+
+def edge_noise_from_raw(raw, edge_mask):
+    """models/utils.py:100-106 with the randn draw supplied: raw [B,2,N,N]."""
+    B, C, N, _ = raw.shape
+    z = torch.tril(raw, -1)
+    z = z + z.transpose(-1, -2)
+    return z.permute(0, 2, 3, 1) * edge_mask.reshape(B, N, N, 1)
+
+
+def draw_step_noise(B, N, node_mask, edge_mask, generator=None, device='cpu', dtype=torch.float32):
+    """Draw order of the reference per step: randn(B,N,3), randn(B,N,6), randn(B,2,N,N)."""
+    rp = torch.randn(B, N, 3, generator=generator, device=device, dtype=dtype)
+    rh = torch.randn(B, N, 6, generator=generator, device=device, dtype=dtype)
+    re = torch.randn(B, 2, N, N, generator=generator, device=device, dtype=dtype)
+    return rp, rh, re
+
+
+def ancestral_sample(denoise_fn, table, z, edge_z, node_mask, edge_mask, raw_noise, temperature=1.0):
+    """sampling.py:565-631 with pred_data=True, pred_edge=True, self_cond='ori'.
+    denoise_fn(x, edge_x, noise_level[B], cond_x, cond_edge_x) -> (pred, edge_pred);
+    raw_noise: list (len = steps) of (rp, rh, re) raw randn draws."""
+    x, ex = z, edge_z
+    B = z.shape[0]
+    cond_x = cond_ex = None
+    x_mean = ex_mean = None
+    for i in range(table.shape[0]):
+        c_x, c_pred, sigma, nl = table[i]
+        pred, epred = denoise_fn(x, ex, torch.ones(B, device=z.device, dtype=z.dtype) * nl, cond_x, cond_ex)
+        cond_x, cond_ex = pred, epred
+        x_mean = c_x * x + c_pred * pred
+        rp, rh, re = raw_noise[i]
+        x = x_mean + sigma * node_noise_from_raw(rp, rh, node_mask) * temperature
+        ex_mean = c_x * ex + c_pred * epred
+        ex = ex_mean + sigma * edge_noise_from_raw(re, edge_mask) * temperature
+    return x_mean, ex_mean
+
+
+def post_process(xh, edge_x, node_mask, edge_mask):
+    """sampling.py:53-97 with inverse scaler factors (1,4,4,1), centered=True, compress_edge=True
+    (utils.py:71-105).  Returns pos f32 [B,N,3], one_hot i64 [B,N,5], fc i64 [B,N,1], bond f32 [B,N,N]."""
+    B, N, _ = xh.shape
+    pos = xh[:, :, :3] * 1 * node_mask
+    h_cat = (xh[:, :, 3:-1] * 4 + 1.) / 2. * node_mask
+    h_int = xh[:, :, -1:] * 4 * node_mask
+    h_edge = (edge_x * 1 + 1.) / 2. * edge_mask.reshape(B, N, N, 1)
+    one_hot = F.one_hot(torch.argmax(h_cat, dim=2), 5) * node_mask
+    fc = torch.round(h_int).long() * node_mask
+    exist = (h_edge[..., 0] >= 0.5).to(xh.dtype)
+    t = h_edge[..., 1] * 3.
+    order = torch.zeros_like(t)
+    order = torch.where(t >= 0.5, torch.ones_like(t), order)
+    order = torch.where(t >= 1.5, torch.full_like(t, 2.), order)
+    order = torch.where(t >= 2.5, torch.full_like(t, 3.), order)
+    return pos, one_hot.long(), fc.long(), exist * order
