@@ -1,0 +1,75 @@
+// C-ABI entry points: context lifetime, error reporting and the GEMM test hook.
+#include <stdarg.h>
+
+#include "../../include/diffspectra_b200.h"
+#include "context.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void ds_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+const char* ds_last_error(void) { return g_err; }
+
+int ds_version(void) { return 100; }
+
+int ds_create(ds_ctx** out, int device, int mode, int spectra_version) {
+  DS_CHECK(out != nullptr, DS_ERR_INVALID, "ds_create: null out");
+  DS_CHECK(mode == 0 || mode == 1, DS_ERR_INVALID, "ds_create: mode must be 0 (fp32) or 1 (bf16), got %d", mode);
+  DS_CHECK(spectra_version >= 0 && spectra_version <= 3, DS_ERR_INVALID, "ds_create: bad spectra_version %d",
+           spectra_version);
+  int ndev = 0;
+  DS_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  DS_CHECK(device >= 0 && device < ndev, DS_ERR_INVALID, "ds_create: device %d out of range (%d visible)", device, ndev);
+  DS_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DS_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  DS_CHECK(prop.major == 10, DS_ERR_UNSUPPORTED,
+           "ds_create: device %d is sm_%d%d; this library is built for sm_100a only (no fallback path)", device,
+           prop.major, prop.minor);
+  DsContext* c = new DsContext();
+  c->device = device;
+  c->mode = mode;
+  c->spectra_version = spectra_version;
+  c->num_sms = prop.multiProcessorCount;
+  int r = gemm_tc_init(c);
+  if (r != DS_OK) {
+    delete c;
+    return r;
+  }
+  *out = reinterpret_cast<ds_ctx*>(c);
+  return DS_OK;
+}
+
+int ds_destroy(ds_ctx* h) {
+  DsContext* c = reinterpret_cast<DsContext*>(h);
+  if (!c) return DS_OK;
+  if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+  delete c;
+  return DS_OK;
+}
+
+long long ds_launch_count(ds_ctx* h) { return reinterpret_cast<DsContext*>(h)->launch_count; }
+
+int ds_gemm(ds_ctx* h, int use_tensor_cores, const void* A, int lda, const void* W, int ldw, const float* bias,
+            const float* addmat, int ldadd, void* out, int ldo, int M, int N, int K, int in_dtype, int out_dtype,
+            int act, void* stream) {
+  DsContext* c = reinterpret_cast<DsContext*>(h);
+  DS_CHECK(c != nullptr, DS_ERR_INVALID, "ds_gemm: null ctx");
+  GemmDesc g;
+  g.A = A; g.W = W; g.bias = bias; g.addmat = addmat; g.out = out;
+  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldadd = ldadd;
+  g.a_dtype = in_dtype; g.out_dtype = out_dtype; g.act = act;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (use_tensor_cores) return gemm_tc_launch(c, g, s);
+  c->launch_count++;
+  return gemm_simt_launch(g, c->mode == 1, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// Shared device helpers and the internal (C++) interface between the translation units of
+// libdiffspectra_b200.so.  Nothing here is part of the C-ABI (see include/diffspectra_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+// ----------------------------------------------------------------------------- error codes (mirrored in the header)
+#define DS_OK 0
+#define DS_ERR_INVALID -1
+#define DS_ERR_CUDA -2
+#define DS_ERR_MISSING_PARAM -3
+#define DS_ERR_UNSUPPORTED -4
+#define DS_ERR_WORKSPACE -5
+
+#define DS_CUDA_CHECK(expr)                                                                       \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ds_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return DS_ERR_CUDA;                                                                         \
+    }                                                                                             \
+  } while (0)
+
+#define DS_CHECK(cond, code, ...) \
+  do {                            \
+    if (!(cond)) {                \
+      ds_set_error(__VA_ARGS__);  \
+      return (code);              \
+    }                             \
+  } while (0)
+
+#define DS_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != DS_OK) return _r; \
+  } while (0)
+
+void ds_set_error(const char* fmt, ...);
+
+// ----------------------------------------------------------------------------- model dimensions (QM9S config)
+// configs/diffspectra_qm9s.py:53-76 — the kernels are specialised for these.
+constexpr int D_NODE = 256;    // model.nf
+constexpr int D_EDGE = 64;     // nf / 4
+constexpr int D_TIME = 1024;   // nf * 4
+constexpr int N_LAYERS = 8;
+constexpr int N_HEADS = 16;
+constexpr int N_XHEADS = 2;                 // adjacency heads
+constexpr int N_SUB = N_HEADS - N_XHEADS;   // 14 learned heads
+constexpr int C_SUB = 18;                   // 256 / 14
+constexpr int C_HEAD = 16;
+constexpr int QK_DIM = N_SUB * C_SUB;       // 252
+constexpr int QKV_LD = 768;                 // q[0,252) pad, k[256,508) pad, v[512,768)
+constexpr int E01_LD = 512;                 // e0[0,252) pad, e1[256,512)
+constexpr int MAX_ATOMS = 64;               // stress config; QM9S has <= 29
+
+// adaLN table layout: one row per molecule (fp32)
+constexpr int ADA_NODE = 0;      // nsh1 nsc1 ng1 nsh2 nsc2 ng2  (6 x 256)
+constexpr int ADA_EDGE = 1536;   // esh1 esc1 eg1 esh2 esc2 eg2  (6 x 64)
+constexpr int ADA_COORD = 1920;  // csh csc                      (2 x 256)
+constexpr int ADA_RBF = 2432;    // scale, shift
+constexpr int ADA_BLK = 2440;    // per-block stride (padded)
+constexpr int ADA_ROOT_RBF = N_LAYERS * ADA_BLK;   // 19520
+constexpr int ADA_LD = 19584;                      // padded row length
+
+// ----------------------------------------------------------------------------- activation / dtype tags
+enum DsAct { ACT_NONE = 0, ACT_SILU = 1, ACT_TANH = 2, ACT_GELU = 3 };
+enum DsDType { DT_F32 = 0, DT_BF16 = 1 };
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ bf16 from_f32<bf16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// kFast = bf16 production mode (approximate SFU maths), !kFast = fp32 validation mode (libm-accurate).
+template <bool kFast>
+__device__ __forceinline__ float act_tanh(float x) {
+  if (kFast) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  }
+  return tanhf(x);
+}
+template <bool kFast>
+__device__ __forceinline__ float act_exp(float x) {
+  return kFast ? __expf(x) : expf(x);
+}
+template <bool kFast>
+__device__ __forceinline__ float act_silu(float x) {
+  if (kFast) return x * (0.5f * act_tanh<true>(0.5f * x) + 0.5f);   // x*sigmoid(x), one MUFU
+  return x / (1.0f + expf(-x));
+}
+__device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <bool kFast>
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_SILU: return act_silu<kFast>(x);
+    case ACT_TANH: return act_tanh<kFast>(x);
+    case ACT_GELU: return act_gelu(x);
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ----------------------------------------------------------------------------- molecule plan (packed ragged layout)
+// node_info[m] = mol << 6 | i          pair_info[p] = mol << 12 | i << 6 | j   (i < j)
+struct Plan {
+  int B, N;              // molecules, padded atom count of the dense interface
+  int Mn, Mp;            // total atoms, total unordered pairs
+  const int* n_atoms;    // [B]
+  const int* noff;       // [B+1]
+  const int* poff;       // [B+1]
+  const uint32_t* node_info;   // [Mn]
+  const uint32_t* pair_info;   // [Mp]
+};
+__device__ __forceinline__ int pair_index(int n, int i, int j) {   // i < j < n, row-major upper triangle
+  return i * n - (i * (i + 1)) / 2 + (j - i - 1);
+}
+
+// ----------------------------------------------------------------------------- GEMM  out = act(A W^T + bias + addmat)
+struct GemmDesc {
+  const void* A;      // [M, K] row-major, leading dim lda (elements); dtype a_dtype
+  const void* W;      // [N, K] row-major, leading dim ldw; same dtype as A
+  const float* bias;  // [N] or null
+  const float* addmat;   // [M, ldadd] fp32 added before the activation, or null
+  void* out;          // [M, N] row-major, leading dim ldo; dtype out_dtype
+  int M, N, K;
+  int lda, ldw, ldo, ldadd;
+  int a_dtype, out_dtype;
+  int act;
+};
+
+struct DsContext;
+int gemm_simt_launch(const GemmDesc& g, bool fast_math, cudaStream_t s);
+int gemm_tc_launch(DsContext* ctx, const GemmDesc& g, cudaStream_t s);   // bf16 in, tcgen05
+int gemm_tc_init(DsContext* ctx);

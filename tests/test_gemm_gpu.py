@@ -1,0 +1,93 @@
+"""Parity of the two GEMM kernels (tcgen05/TMA bf16 and CUDA-core fp32) against torch matmul."""
+import ctypes
+
+import pytest
+import torch
+
+from diffspectra_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+ACTS = {L.ACT_NONE: lambda x: x, L.ACT_SILU: torch.nn.functional.silu, L.ACT_TANH: torch.tanh,
+        L.ACT_GELU: torch.nn.functional.gelu}
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    h = ctypes.c_void_p()
+    L.check(L.lib().ds_create(ctypes.byref(h), 0, L.MODE_BF16, 3), 'ds_create')
+    yield h
+    L.lib().ds_destroy(h)
+
+
+def run_gemm(ctx, tc, A, W, bias, addmat, out, act, M, N, K):
+    in_dt = L.DT_BF16 if A.dtype == torch.bfloat16 else L.DT_F32
+    out_dt = L.DT_BF16 if out.dtype == torch.bfloat16 else L.DT_F32
+    L.check(L.lib().ds_gemm(ctx, int(tc), L.ptr(A), A.stride(0), L.ptr(W), W.stride(0), L.ptr(bias), L.ptr(addmat),
+                            addmat.stride(0) if addmat is not None else 0, L.ptr(out), out.stride(0), M, N, K,
+                            in_dt, out_dt, act, L.stream_ptr()), 'ds_gemm')
+    torch.cuda.synchronize()
+
+
+SHAPES = [  # (M, N, K) — the shapes the denoiser uses plus ragged tails
+    (128, 64, 64), (300, 64, 128), (1000, 512, 64), (257, 768, 256), (513, 256, 512), (129, 16, 64),
+    (4, 19584, 1024), (77, 128, 192), (2000, 256, 256), (64, 256, 768), (5, 256, 44416), (1, 1024, 1024),
+    (40000, 256, 256), (333, 500, 64), (150, 32, 64),
+]
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+def test_gemm_tc_matches_torch(ctx, M, N, K):
+    g = torch.Generator(device='cuda').manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn(M, K, device='cuda', generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device='cuda', generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g) * 0.1
+    ref = A.float() @ W.float().t() + bias
+    out = torch.full((M, N), float('nan'), device='cuda')
+    run_gemm(ctx, True, A, W, bias, None, out, L.ACT_NONE, M, N, K)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), (M, N, K, err)
+
+
+@pytest.mark.parametrize('act', [L.ACT_SILU, L.ACT_TANH, L.ACT_GELU])
+@pytest.mark.parametrize('out_dtype', [torch.float32, torch.bfloat16])
+def test_gemm_tc_epilogue(ctx, act, out_dtype):
+    M, N, K = 777, 508, 128
+    g = torch.Generator(device='cuda').manual_seed(act)
+    A = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    W = (torch.randn(N, K, device='cuda', generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g) * 0.1
+    add = torch.randn(M, N, device='cuda', generator=g)
+    ref = ACTS[act](A.float() @ W.float().t() + bias + add)
+    buf = torch.full((M, 512), -7.0, device='cuda', dtype=out_dtype)      # ldo > N: padding must stay untouched
+    run_gemm(ctx, True, A, W, bias, add, buf, act, M, N, K)
+    tol = 2e-2 if out_dtype == torch.bfloat16 else 5e-3
+    assert (buf[:, :N].float() - ref).abs().max().item() < tol
+    assert (buf[:, N:] == -7.0).all()
+
+
+def test_gemm_tc_strided_views(ctx):
+    """A and out as column slices of wider buffers (how the denoiser writes atom_hids / edge_hids)."""
+    M, N, K = 1000, 16, 64
+    g = torch.Generator(device='cuda').manual_seed(5)
+    Xbuf = torch.randn(M, 128, device='cuda', generator=g).bfloat16()
+    A = Xbuf[:, 64:]
+    W = (torch.randn(N, K, device='cuda', generator=g) / 8).bfloat16()
+    hid = torch.zeros(M, 192, device='cuda', dtype=torch.bfloat16)
+    out = hid[:, 80:96]
+    run_gemm(ctx, True, A, W, None, None, out, L.ACT_NONE, M, N, K)
+    ref = A.float() @ W.float().t()
+    assert (out.float() - ref).abs().max().item() < 2e-2
+    assert (hid[:, :80] == 0).all() and (hid[:, 96:] == 0).all()
+
+
+@pytest.mark.parametrize('M,N,K', [(100, 64, 68), (33, 1024, 17), (257, 6, 128), (500, 256, 640), (64, 128, 20)])
+def test_gemm_simt_fp32(ctx, M, N, K):
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    A = torch.randn(M, K, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g) / K ** 0.5
+    bias = torch.randn(N, device='cuda', generator=g)
+    ref = (A.double() @ W.double().t() + bias.double()).float()
+    out = torch.empty(M, N, device='cuda')
+    run_gemm(ctx, False, A, W, bias, None, out, L.ACT_NONE, M, N, K)
+    assert (out - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
