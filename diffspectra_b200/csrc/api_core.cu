@@ -4,6 +4,9 @@
 #include "../../include/diffspectra_b200.h"
 #include "context.cuh"
 
+DsContext* ds_ctx_alloc();
+void ds_ctx_free(DsContext* c);
+
 static thread_local char g_err[1024] = "";
 
 void ds_set_error(const char* fmt, ...) {
@@ -33,14 +36,14 @@ int ds_create(ds_ctx** out, int device, int mode, int spectra_version) {
   DS_CHECK(prop.major == 10, DS_ERR_UNSUPPORTED,
            "ds_create: device %d is sm_%d%d; this library is built for sm_100a only (no fallback path)", device,
            prop.major, prop.minor);
-  DsContext* c = new DsContext();
+  DsContext* c = ds_ctx_alloc();
   c->device = device;
   c->mode = mode;
   c->spectra_version = spectra_version;
   c->num_sms = prop.multiProcessorCount;
   int r = gemm_tc_init(c);
   if (r != DS_OK) {
-    delete c;
+    ds_ctx_free(c);
     return r;
   }
   *out = reinterpret_cast<ds_ctx*>(c);
@@ -51,7 +54,7 @@ int ds_destroy(ds_ctx* h) {
   DsContext* c = reinterpret_cast<DsContext*>(h);
   if (!c) return DS_OK;
   if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
-  delete c;
+  ds_ctx_free(c);
   return DS_OK;
 }
 

@@ -1,0 +1,338 @@
+// C-ABI entry points of the sampling hot path: weights, molecule plan, SpecFormer context, one denoiser call on
+// dense (reference-shaped) tensors, the graph-captured sampling loop, a stand-alone sampler step and post_process.
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/diffspectra_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+struct GraphKey {     // everything that is baked into the captured step graph
+  const void *ws, *plan, *ctx_emb, *coef, *raw_pos, *raw_h, *raw_e, *pw_blob;
+  int B, N, Mn, Mp;
+  unsigned long long seed;
+  long long gid_base;
+  float temperature;
+  int first_step;   // external-noise indexing is relative to the segment start
+};
+struct CtxFull : DsContext {
+  PackedWeights pw;
+  GraphKey gkey;
+};
+// DsContext is allocated as CtxFull in api_core.cu (ds_create) — see ds_ctx_alloc below.
+
+inline CtxFull* full(ds_ctx* h) { return reinterpret_cast<CtxFull*>(h); }
+
+// plan blob layout (device, int32): n_atoms[B] | noff[B+1] | poff[B+1] | node_info[Mn_max] | pair_info[Mp_max]
+struct PlanLayout {
+  size_t n_atoms, noff, poff, node_info, pair_info, total;
+};
+PlanLayout plan_layout(int B, int N) {
+  PlanLayout L;
+  auto al = [](size_t x) { return (x + 63) & ~size_t(63); };
+  size_t o = 0;
+  L.n_atoms = o; o = al(o + size_t(B) * 4);
+  L.noff = o; o = al(o + size_t(B + 1) * 4);
+  L.poff = o; o = al(o + size_t(B + 1) * 4);
+  L.node_info = o; o = al(o + size_t(B) * N * 4);
+  L.pair_info = o; o = al(o + size_t(B) * N * (N - 1) / 2 * 4 + 4);
+  L.total = o;
+  return L;
+}
+
+int make_plan(const void* plan_dev, int B, int N, int Mn, int Mp, Plan* p) {
+  DS_CHECK(plan_dev != nullptr, DS_ERR_INVALID, "plan buffer is null");
+  const PlanLayout L = plan_layout(B, N);
+  const uint8_t* base = static_cast<const uint8_t*>(plan_dev);
+  p->B = B; p->N = N; p->Mn = Mn; p->Mp = Mp;
+  p->n_atoms = reinterpret_cast<const int*>(base + L.n_atoms);
+  p->noff = reinterpret_cast<const int*>(base + L.noff);
+  p->poff = reinterpret_cast<const int*>(base + L.poff);
+  p->node_info = reinterpret_cast<const uint32_t*>(base + L.node_info);
+  p->pair_info = reinterpret_cast<const uint32_t*>(base + L.pair_info);
+  return DS_OK;
+}
+
+struct LoopWs {
+  float *xs, *es, *pred_x, *pred_e, *xmean, *emean;
+  int* step;
+};
+size_t loop_ws_carve(Arena& a, LoopWs& w, int Mn, int Mp) {
+  const size_t mn = Mn > 0 ? Mn : 1, mp = Mp > 0 ? Mp : 1;
+  const size_t start = a.off;
+  w.xs = static_cast<float*>(a.take(mn * 9 * 4));
+  w.es = static_cast<float*>(a.take(mp * 2 * 4));
+  w.pred_x = static_cast<float*>(a.take(mn * 9 * 4));
+  w.pred_e = static_cast<float*>(a.take(mp * 2 * 4));
+  w.xmean = static_cast<float*>(a.take(mn * 9 * 4));
+  w.emean = static_cast<float*>(a.take(mp * 2 * 4));
+  w.step = static_cast<int*>(a.take(16));
+  return a.off - start;
+}
+
+}  // namespace
+
+DsContext* ds_ctx_alloc() { return new CtxFull(); }
+void ds_ctx_free(DsContext* c) { delete static_cast<CtxFull*>(c); }
+
+extern "C" {
+
+size_t ds_packed_weights_bytes(ds_ctx* h) { return packed_weights_bytes(full(h)); }
+
+int ds_pack_weights(ds_ctx* h, const char* const* names, const void* const* ptrs, int n, void* blob, size_t blob_bytes,
+                    void* stream) {
+  CtxFull* c = full(h);
+  DS_CHECK(c != nullptr && names != nullptr && ptrs != nullptr, DS_ERR_INVALID, "ds_pack_weights: null argument");
+  c->pw.valid = false;
+  if (c->step_graph) {   // packed pointers may have moved: drop the cached step graph
+    cudaGraphExecDestroy(c->step_graph);
+    c->step_graph = nullptr;
+  }
+  return pack_weights(c, names, ptrs, n, blob, blob_bytes, &c->pw, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t ds_plan_bytes(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  return plan_layout(B, N).total;
+}
+
+int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_dev, int* Mn_out, int* Mp_out, void* stream) {
+  DS_CHECK(h && n_atoms_host && plan_dev && Mn_out && Mp_out, DS_ERR_INVALID, "ds_plan_build: null argument");
+  DS_CHECK(B > 0 && B < (1 << 19), DS_ERR_INVALID, "ds_plan_build: B=%d out of range", B);
+  DS_CHECK(N > 0 && N <= MAX_ATOMS, DS_ERR_INVALID, "ds_plan_build: N=%d out of range (1..%d)", N, MAX_ATOMS);
+  const PlanLayout L = plan_layout(B, N);
+  std::vector<uint8_t> host(L.total, 0);
+  int* na = reinterpret_cast<int*>(host.data() + L.n_atoms);
+  int* noff = reinterpret_cast<int*>(host.data() + L.noff);
+  int* poff = reinterpret_cast<int*>(host.data() + L.poff);
+  uint32_t* ni = reinterpret_cast<uint32_t*>(host.data() + L.node_info);
+  uint32_t* pi = reinterpret_cast<uint32_t*>(host.data() + L.pair_info);
+  int mn = 0, mp = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = n_atoms_host[b];
+    DS_CHECK(n >= 1 && n <= N, DS_ERR_INVALID, "ds_plan_build: n_atoms[%d]=%d outside 1..%d", b, n, N);
+    na[b] = n;
+    noff[b] = mn;
+    poff[b] = mp;
+    for (int i = 0; i < n; ++i) ni[mn + i] = (static_cast<uint32_t>(b) << 6) | i;
+    int q = mp;
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j) pi[q++] = (static_cast<uint32_t>(b) << 12) | (i << 6) | j;
+    mn += n;
+    mp += n * (n - 1) / 2;
+  }
+  noff[B] = mn;
+  poff[B] = mp;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DS_CUDA_CHECK(cudaMemcpyAsync(plan_dev, host.data(), L.total, cudaMemcpyHostToDevice, s));
+  DS_CUDA_CHECK(cudaStreamSynchronize(s));   // host staging buffer dies at return
+  *Mn_out = mn;
+  *Mp_out = mp;
+  return DS_OK;
+}
+
+size_t ds_workspace_bytes(ds_ctx* h, int B, int Mn, int Mp) {
+  CtxFull* c = full(h);
+  if (!c || B <= 0) return 0;
+  Arena a{nullptr, 0, 0, true};
+  DenoiseWs dw;
+  LoopWs lw;
+  denoise_ws_carve(a, dw, B, Mn, Mp, ds_is_bf16(c));
+  loop_ws_carve(a, lw, Mn, Mp);
+  a.take(size_t(B) * D_TIME * 4);   // ctx embedding when the loop computes it
+  return a.off + 1024;
+}
+
+size_t ds_specformer_workspace_bytes(ds_ctx* h, int B) {
+  CtxFull* c = full(h);
+  if (!c || B <= 0) return 0;
+  static const int kLen[3] = {701, 3501, 3501}, kPatch[3] = {20, 50, 50}, kStride[3] = {10, 25, 25};
+  int Q = 0;
+  for (int t = 0; t < 3; ++t)
+    if (c->spectra_version == 3 || c->spectra_version == t) Q += (kLen[t] - kPatch[t]) / kStride[t] + 1;
+  int Bc = static_cast<int>((size_t(1) << 30) / (size_t(16) * Q * Q * 4));
+  if (Bc < 1) Bc = 1;
+  if (Bc > B) Bc = B;
+  Arena a{nullptr, 0, 0, true};
+  SpecWs w;
+  spec_ws_carve(a, w, Bc, Q, ds_is_bf16(c));
+  return a.off + 1024;
+}
+
+int ds_specformer_ctx(ds_ctx* h, const float* uv, const float* ir, const float* raman, int B, float* ctx_out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  CtxFull* c = full(h);
+  DS_CHECK(c && ctx_out && workspace, DS_ERR_INVALID, "ds_specformer_ctx: null argument");
+  const float* all[3] = {uv, ir, raman};
+  const float* used[3] = {nullptr, nullptr, nullptr};
+  if (c->spectra_version == 3) {
+    used[0] = uv; used[1] = ir; used[2] = raman;
+  } else {
+    used[0] = all[c->spectra_version];
+  }
+  return specformer_ctx(c, c->pw, used, B, ctx_out, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ds_denoise(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp, const float* x, const float* edge_x,
+               const float* cond_x, const float* cond_edge_x, const float* noise_level, const float* ctx_emb,
+               float* out_x, float* out_edge, void* workspace, size_t workspace_bytes, void* stream) {
+  CtxFull* c = full(h);
+  DS_CHECK(c && x && edge_x && noise_level && ctx_emb && out_x && out_edge && workspace, DS_ERR_INVALID,
+           "ds_denoise: null argument");
+  Plan plan;
+  DS_TRY(make_plan(plan_dev, B, N, Mn, Mp, &plan));
+  Arena a{static_cast<uint8_t*>(workspace), 0, workspace_bytes, false};
+  DenoiseWs dw;
+  LoopWs lw;
+  denoise_ws_carve(a, dw, B, Mn, Mp, ds_is_bf16(c));
+  loop_ws_carve(a, lw, Mn, Mp);
+  DS_CHECK(a.off <= workspace_bytes, DS_ERR_WORKSPACE, "ds_denoise: workspace too small (%zu < %zu)", workspace_bytes, a.off);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DS_TRY(launch_pack_dense(c, plan, x, edge_x, lw.xs, lw.es, s));
+  const float* cx = nullptr;
+  const float* ce = nullptr;
+  if (cond_x) {
+    DS_TRY(launch_pack_dense(c, plan, cond_x, cond_edge_x, lw.xmean, lw.emean, s));
+    cx = lw.xmean;
+    ce = lw.emean;
+  }
+  StepRef sr{nullptr, nullptr};
+  DS_TRY(denoise_packed(c, c->pw, plan, lw.xs, lw.es, cx, ce, noise_level, sr, ctx_emb, lw.pred_x, lw.pred_e, dw, s));
+  DS_TRY(launch_unpack_dense(c, plan, lw.pred_x, lw.pred_e, out_x, out_edge, s));
+  return DS_OK;
+}
+
+int ds_sample_loop(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp, const float* z, const float* edge_z,
+                   const float* ctx_emb, const float* coef_table, int first_step, int steps, const float* raw_pos,
+                   const float* raw_h, const float* raw_e, unsigned long long seed, long long gid_base, float temperature,
+                   int use_graph, float* x_mean_out, float* edge_mean_out, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  CtxFull* c = full(h);
+  DS_CHECK(c && ctx_emb && coef_table && x_mean_out && edge_mean_out && workspace, DS_ERR_INVALID,
+           "ds_sample_loop: null argument");
+  DS_CHECK(steps > 0 && first_step >= 0, DS_ERR_INVALID, "ds_sample_loop: steps must be positive, first_step >= 0");
+  DS_CHECK((raw_pos == nullptr) == (raw_h == nullptr) && (raw_pos == nullptr) == (raw_e == nullptr), DS_ERR_INVALID,
+           "ds_sample_loop: raw_pos/raw_h/raw_e must all be given (external noise) or all null (Philox)");
+  DS_CHECK((z == nullptr) == (edge_z == nullptr), DS_ERR_INVALID, "ds_sample_loop: z and edge_z go together");
+  Plan plan;
+  DS_TRY(make_plan(plan_dev, B, N, Mn, Mp, &plan));
+  Arena a{static_cast<uint8_t*>(workspace), 0, workspace_bytes, false};
+  DenoiseWs dw;
+  LoopWs lw;
+  denoise_ws_carve(a, dw, B, Mn, Mp, ds_is_bf16(c));
+  loop_ws_carve(a, lw, Mn, Mp);
+  DS_CHECK(a.off <= workspace_bytes, DS_ERR_WORKSPACE, "ds_sample_loop: workspace too small (%zu < %zu)", workspace_bytes, a.off);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // external noise arrays hold the draws of THIS segment only: raw index = step - first_step
+  NoiseSrc ns{raw_pos, raw_h, raw_e, seed, gid_base, 0, first_step};
+
+  if (first_step == 0) {
+    // initial state: supplied z_T (reference: sampling.py:442-447) or Philox draw index -1
+    if (z) {
+      DS_TRY(launch_pack_dense(c, plan, z, edge_z, lw.xs, lw.es, s));
+    } else {
+      NoiseSrc ns0{nullptr, nullptr, nullptr, seed, gid_base, 0, 0};
+      DS_TRY(launch_init_noise(c, plan, lw.xs, lw.es, ns0, s));
+    }
+    // self-conditioning carry starts at zero == the reference's cond_x=None branch (dmt.py:332-335)
+    DS_CUDA_CHECK(cudaMemsetAsync(lw.pred_x, 0, size_t(Mn) * 9 * 4, s));
+    DS_CUDA_CHECK(cudaMemsetAsync(lw.pred_e, 0, size_t(Mp > 0 ? Mp : 1) * 2 * 4, s));
+  }   // else: continue from the state a previous segment left in the workspace
+  DS_CUDA_CHECK(cudaMemcpyAsync(lw.step, &first_step, 4, cudaMemcpyHostToDevice, s));
+  StepRef sr{coef_table, lw.step};
+
+  auto one_step = [&]() -> int {
+    DS_TRY(denoise_packed(c, c->pw, plan, lw.xs, lw.es, lw.pred_x, lw.pred_e, nullptr, sr, ctx_emb, lw.pred_x, lw.pred_e, dw, s));
+    DS_TRY(launch_sampler_step(c, plan, lw.xs, lw.es, lw.pred_x, lw.pred_e, lw.xmean, lw.emean, sr, 0, ns, temperature, s));
+    DS_TRY(launch_step_inc(c, lw.step, s));
+    return DS_OK;
+  };
+
+  if (!use_graph) {
+    for (int i = 0; i < steps; ++i) DS_TRY(one_step());
+  } else {
+    // One step is captured once (all kernels read the step index from device memory) and replayed `steps` times.
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.ws = workspace; key.plan = plan_dev; key.ctx_emb = ctx_emb; key.coef = coef_table;
+    key.raw_pos = raw_pos; key.raw_h = raw_h; key.raw_e = raw_e; key.pw_blob = c->pw.w_ada;
+    key.B = B; key.N = N; key.Mn = Mn; key.Mp = Mp; key.seed = seed; key.gid_base = gid_base; key.temperature = temperature;
+    key.first_step = raw_pos ? first_step : 0;
+    if (c->step_graph == nullptr || memcmp(&c->gkey, &key, sizeof(key)) != 0) {
+      if (c->step_graph) {
+        cudaGraphExecDestroy(c->step_graph);
+        c->step_graph = nullptr;
+      }
+      const long long before = c->launch_count;
+      cudaGraph_t graph = nullptr;
+      DS_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int r = one_step();
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (r != DS_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return r;
+      }
+      DS_CUDA_CHECK(ce);
+      c->step_graph_launches = c->launch_count - before;
+      c->launch_count = before;
+      cudaError_t ie = cudaGraphInstantiate(&c->step_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      DS_CUDA_CHECK(ie);
+      c->gkey = key;
+    }
+    for (int i = 0; i < steps; ++i) {
+      DS_CUDA_CHECK(cudaGraphLaunch(c->step_graph, s));
+      c->launch_count += c->step_graph_launches;
+    }
+  }
+  // the reference returns the MEANS of the last step (sampling.py:628-629)
+  DS_TRY(launch_unpack_dense(c, plan, lw.xmean, lw.emean, x_mean_out, edge_mean_out, s));
+  return DS_OK;
+}
+
+int ds_sampler_step(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp, float* x, float* edge_x,
+                    const float* pred, const float* edge_pred, const float* coef_row, const float* raw_pos,
+                    const float* raw_h, const float* raw_e, unsigned long long seed, long long gid_base, int step_index,
+                    float temperature, float* x_mean_out, float* edge_mean_out, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  CtxFull* c = full(h);
+  DS_CHECK(c && x && edge_x && pred && edge_pred && coef_row && workspace, DS_ERR_INVALID, "ds_sampler_step: null argument");
+  Plan plan;
+  DS_TRY(make_plan(plan_dev, B, N, Mn, Mp, &plan));
+  Arena a{static_cast<uint8_t*>(workspace), 0, workspace_bytes, false};
+  LoopWs lw;
+  loop_ws_carve(a, lw, Mn, Mp);
+  DS_CHECK(a.off <= workspace_bytes, DS_ERR_WORKSPACE, "ds_sampler_step: workspace too small (%zu < %zu)", workspace_bytes, a.off);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DS_TRY(launch_pack_dense(c, plan, x, edge_x, lw.xs, lw.es, s));
+  DS_TRY(launch_pack_dense(c, plan, pred, edge_pred, lw.pred_x, lw.pred_e, s));
+  // coef_row points at the row of this step; external noise pointers at this step's draws -> index 0 for both,
+  // while Philox is keyed by the true step_index.
+  NoiseSrc ns{raw_pos, raw_h, raw_e, seed, gid_base, step_index, 0};
+  StepRef sr{coef_row, nullptr};
+  DS_TRY(launch_sampler_step(c, plan, lw.xs, lw.es, lw.pred_x, lw.pred_e, lw.xmean, lw.emean, sr, 0, ns, temperature, s));
+  DS_TRY(launch_unpack_dense(c, plan, lw.xs, lw.es, x, edge_x, s));
+  if (x_mean_out) DS_TRY(launch_unpack_dense(c, plan, lw.xmean, lw.emean, x_mean_out, edge_mean_out, s));
+  return DS_OK;
+}
+
+int ds_post_process(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp, const float* x_mean, const float* edge_mean,
+                    float* pos, int* atom_type, int* formal_charge, float* bond, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  CtxFull* c = full(h);
+  DS_CHECK(c && x_mean && edge_mean && pos && atom_type && formal_charge && bond && workspace, DS_ERR_INVALID,
+           "ds_post_process: null argument");
+  Plan plan;
+  DS_TRY(make_plan(plan_dev, B, N, Mn, Mp, &plan));
+  Arena a{static_cast<uint8_t*>(workspace), 0, workspace_bytes, false};
+  LoopWs lw;
+  loop_ws_carve(a, lw, Mn, Mp);
+  DS_CHECK(a.off <= workspace_bytes, DS_ERR_WORKSPACE, "ds_post_process: workspace too small");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DS_TRY(launch_pack_dense(c, plan, x_mean, edge_mean, lw.xs, lw.es, s));
+  return launch_post_process(c, plan, lw.xs, lw.es, pos, atom_type, formal_charge, bond, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,795 @@
+// Graph-side kernels of the DMT denoiser on the packed ragged layout (atoms / unordered pairs / directed
+// edges), plus the host orchestration of one denoiser call (denoise_packed).
+//
+// Maths = SURVEY.md Appendix A, i.e. models/dmt.py:306-413 (DMT.forward), :122-174 (EquivariantMixBlock),
+// :37-60 (MultiCondEquiUpdate), models/layers.py:131-186 (TransMixLayer), :291-334 (Cond. Gaussian RBF),
+// :337-347 (CoorsNorm), models/utils.py:38-45,118-144.  Algebraic restructuring vs the reference:
+//   * every projection of time_emb is computed once per molecule (the "adaLN table"), not per edge;
+//   * edge features are bit-symmetric in the reference, so they live per unordered pair (i<j);
+//   * node2edge_lin(h_r + h_c) and the h_row / h_col parts of equi_update.input_lin are applied per atom;
+//   * the four host synchronisations of the reference (nonzero, dense_to_sparse, distances.sum()==0,
+//     isnan) become a precomputed plan and two device-side flags.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr float kLnEps = 1e-6f;
+
+template <bool kFast>
+__device__ __forceinline__ float inv_std(float var) {
+  return kFast ? rsqrtf(var + kLnEps) : 1.0f / sqrtf(var + kLnEps);
+}
+
+__device__ __forceinline__ void unpack_pair(uint32_t info, int& mol, int& i, int& j) {
+  mol = info >> 12;
+  i = (info >> 6) & 63;
+  j = info & 63;
+}
+
+// gaussian() of models/layers.py:291-295 with pi = 3.14159
+template <bool kFast>
+__device__ __forceinline__ float rbf_value(float x, int k, const float* __restrict__ means, const float* __restrict__ stds) {
+  if (k == 0) return x;
+  const float a = 2.5066272160016134f;   // (2*3.14159)**0.5
+  const float mean = means[k - 1];
+  const float sd = fabsf(stds[k - 1]) + 1e-5f;
+  const float t = (x - mean) / sd;
+  return act_exp<kFast>(-0.5f * (t * t)) / (a * sd);
+}
+
+// ----------------------------------------------------------------------------- time embedding features
+// LearnedSinusodialposEmb (layers.py:283-288) -> Linear(17,1024) -> GELU   (dmt.py:249-257)
+template <typename AT>
+__global__ void __launch_bounds__(256) k_time_feat(const float* __restrict__ nl, StepRef sr, const float* __restrict__ freq,
+                                                   const float* __restrict__ w1, const float* __restrict__ b1,
+                                                   AT* __restrict__ out) {
+  __shared__ float f[17];
+  const int b = blockIdx.x;
+  const float x = nl ? nl[b] : sr.coef[(*sr.step) * 4 + 3];
+  if (threadIdx.x < 17) {
+    const int t = threadIdx.x;
+    float v;
+    if (t == 0) v = x;
+    else {
+      const float fr = ((x * freq[(t - 1) & 7]) * 2.0f) * 3.14159265358979323846f;
+      v = (t <= 8) ? sinf(fr) : cosf(fr);
+    }
+    f[t] = v;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < D_TIME; o += 256) {
+    float acc = b1[o];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) acc = fmaf(w1[o * 17 + k], f[k], acc);
+    out[static_cast<size_t>(b) * D_TIME + o] = from_f32<AT>(act_gelu(acc));
+  }
+}
+
+// ----------------------------------------------------------------------------- root embeddings
+// h = node_emb([h(6) | cond_h(6)])  (dmt.py:343-345,376); pos = x[:, :3]
+template <typename AT>
+__global__ void __launch_bounds__(256) k_root_nodes(int Mn, const float* __restrict__ xs, const float* __restrict__ cond,
+                                                    const float* __restrict__ w, const float* __restrict__ b,
+                                                    float* __restrict__ h, AT* __restrict__ hb, AT* __restrict__ ahid,
+                                                    float* __restrict__ pos) {
+  __shared__ float in[12];
+  const int m = blockIdx.x;
+  const int t = threadIdx.x;
+  if (t < 6) in[t] = xs[m * 9 + 3 + t];
+  else if (t < 12) in[t] = cond ? cond[m * 9 + 3 + (t - 6)] : 0.f;
+  if (t < 3) pos[m * 3 + t] = xs[m * 9 + t];
+  __syncthreads();
+  float acc = b[t];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc = fmaf(w[t * 12 + k], in[k], acc);
+  h[static_cast<size_t>(m) * D_NODE + t] = acc;
+  hb[static_cast<size_t>(m) * D_NODE + t] = from_f32<AT>(acc);
+  ahid[static_cast<size_t>(m) * 768 + t] = from_f32<AT>(acc);
+}
+
+// adjacency heads from the self-conditioning inputs (dmt.py:337-340, models/utils.py:118-126) and the
+// batch-global "all conditioning distances are zero" predicate (dmt.py:364)
+__global__ void k_root_pair_flags(Plan plan, const float* __restrict__ cond, const float* __restrict__ cond_e,
+                                  uint8_t* __restrict__ pflags, int* __restrict__ flags) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  bool nz = false;
+  if (p < plan.Mp) {
+    int mol, i, j;
+    unpack_pair(plan.pair_info[p], mol, i, j);
+    float r0 = 0.f;
+    bool a2 = true;
+    if (cond) {
+      const int base = plan.noff[mol];
+      const float* ci = cond + static_cast<size_t>(base + i) * 9;
+      const float* cj = cond + static_cast<size_t>(base + j) * 9;
+      const float dx = ci[0] - cj[0], dy = ci[1] - cj[1], dz = ci[2] - cj[2];
+      r0 = dx * dx + dy * dy + dz * dz;
+      a2 = cond_e[p * 2] >= 0.0f;
+    }
+    const bool asp = r0 <= 2.0f;
+    pflags[p] = (a2 ? 1 : 0) | (asp ? 2 : 0);
+    nz = !(r0 == 0.f);
+  }
+  if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(&flags[0], 1);
+}
+
+// e = edge_emb([edge_x(2) | cond_edge(2) | RBF_root(r0)(64)])   (dmt.py:363-377)
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_root_pairs(Plan plan, const float* __restrict__ es, const float* __restrict__ cond,
+                                                    const float* __restrict__ cond_e, const float* __restrict__ ada,
+                                                    const int* __restrict__ flags, const float* __restrict__ means,
+                                                    const float* __restrict__ stds, const float* __restrict__ w,
+                                                    const float* __restrict__ b, float* __restrict__ e,
+                                                    AT* __restrict__ X, AT* __restrict__ ehid) {
+  __shared__ float in[4][68];
+  const int pl = threadIdx.x >> 6, k = threadIdx.x & 63;
+  const int p = blockIdx.x * 4 + pl;
+  const bool valid = p < plan.Mp;
+  if (valid) {
+    int mol, i, j;
+    unpack_pair(plan.pair_info[p], mol, i, j);
+    if (k < 2) in[pl][k] = es[p * 2 + k];
+    else if (k < 4) in[pl][k] = cond_e ? cond_e[p * 2 + (k - 2)] : 0.f;
+    float d0 = 0.f;
+    if (flags[0] != 0) {
+      const int base = plan.noff[mol];
+      const float* ci = cond + static_cast<size_t>(base + i) * 9;
+      const float* cj = cond + static_cast<size_t>(base + j) * 9;
+      const float dx = ci[0] - cj[0], dy = ci[1] - cj[1], dz = ci[2] - cj[2];
+      const float r0 = dx * dx + dy * dy + dz * dz;
+      const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + ADA_ROOT_RBF;
+      const float x = r0 * (ar[0] + 1.0f) + ar[1];
+      d0 = rbf_value<kFast>(x, k, means, stds);
+    }
+    in[pl][4 + k] = d0;
+  }
+  __syncthreads();
+  if (!valid) return;
+  float acc = b[k];
+#pragma unroll 4
+  for (int c = 0; c < 68; ++c) acc = fmaf(w[k * 68 + c], in[pl][c], acc);
+  e[static_cast<size_t>(p) * D_EDGE + k] = acc;
+  X[static_cast<size_t>(p) * 128 + 64 + k] = from_f32<AT>(acc);
+  ehid[static_cast<size_t>(p) * 192 + k] = from_f32<AT>(acc);
+}
+
+// ----------------------------------------------------------------------------- per-block kernels
+// X[:, 0:64] = RBF_l(|pos_i - pos_j|^2)   (dmt.py:136-138)
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict__ pos, const float* __restrict__ ada, int l,
+                                             const float* __restrict__ means, const float* __restrict__ stds,
+                                             AT* __restrict__ X) {
+  const int p = blockIdx.x * 4 + (threadIdx.x >> 6), k = threadIdx.x & 63;
+  if (p >= plan.Mp) return;
+  int mol, i, j;
+  unpack_pair(plan.pair_info[p], mol, i, j);
+  const int base = plan.noff[mol];
+  const float* pi = pos + static_cast<size_t>(base + i) * 3;
+  const float* pj = pos + static_cast<size_t>(base + j) * 3;
+  const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
+  const float r2 = dx * dx + dy * dy + dz * dz;
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_RBF;
+  const float x = r2 * (ar[0] + 1.0f) + ar[1];
+  X[static_cast<size_t>(p) * 128 + k] = from_f32<AT>(rbf_value<kFast>(x, k, means, stds));
+}
+
+// 64-wide LayerNorm + modulate, one warp per row, lane owns channels (2*lane, 2*lane+1)
+template <bool kFast>
+__device__ __forceinline__ void ln64_mod(float& v0, float& v1, const float* __restrict__ shift, const float* __restrict__ scale,
+                                         int lane) {
+  const float mean = warp_sum(v0 + v1) * (1.0f / 64.0f);
+  const float d0 = v0 - mean, d1 = v1 - mean;
+  const float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / 64.0f);
+  const float is = inv_std<kFast>(var);
+  const float2 sh = *reinterpret_cast<const float2*>(shift + 2 * lane);
+  const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * lane);
+  v0 = (d0 * is) * (1.0f + sc.x) + sh.x;
+  v1 = (d1 * is) * (1.0f + sc.y) + sh.y;
+}
+
+template <typename AT>
+__device__ __forceinline__ void store2(AT* p, float a, float b);
+template <>
+__device__ __forceinline__ void store2<float>(float* p, float a, float b) {
+  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+template <>
+__device__ __forceinline__ void store2<bf16>(bf16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+template <typename AT>
+__device__ __forceinline__ void store4(AT* p, float a, float b, float c, float d) {
+  store2<AT>(p, a, b);
+  store2<AT>(p + 2, c, d);
+}
+template <typename AT>
+__device__ __forceinline__ float4 load4(const AT* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+// ea = modulate(LN(edge_emb_l([dist | e])), esh1, esc1)    (dmt.py:139,149)
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_pair_ln1(Plan plan, const float* __restrict__ y1, const float* __restrict__ ada, int l,
+                                                  AT* __restrict__ ea) {
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= plan.Mp) return;
+  const int mol = plan.pair_info[p] >> 12;
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_EDGE;
+  const float2 v = *reinterpret_cast<const float2*>(y1 + static_cast<size_t>(p) * 64 + 2 * lane);
+  float v0 = v.x, v1 = v.y;
+  ln64_mod<kFast>(v0, v1, ar + 0, ar + 64, lane);
+  store2<AT>(ea + static_cast<size_t>(p) * 64 + 2 * lane, v0, v1);
+}
+
+// 256-wide LayerNorm + modulate, one warp per row; lane owns channels [4*lane, 4*lane+4) and [128+4*lane, ...)
+template <bool kFast>
+__device__ __forceinline__ void ln256_mod(float (&v)[8], const float* __restrict__ shift, const float* __restrict__ scale, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / 256.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] -= mean;
+    q += v[i] * v[i];
+  }
+  const float var = warp_sum(q) * (1.0f / 256.0f);
+  const float is = inv_std<kFast>(var);
+  const float4 sh0 = *reinterpret_cast<const float4*>(shift + 4 * lane);
+  const float4 sh1 = *reinterpret_cast<const float4*>(shift + 128 + 4 * lane);
+  const float4 sc0 = *reinterpret_cast<const float4*>(scale + 4 * lane);
+  const float4 sc1 = *reinterpret_cast<const float4*>(scale + 128 + 4 * lane);
+  const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+  const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (v[i] * is) * (1.0f + scv[i]) + shv[i];
+}
+
+__device__ __forceinline__ void load8(const float* row, int lane, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(row + 4 * lane);
+  const float4 b = *reinterpret_cast<const float4*>(row + 128 + 4 * lane);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename AT>
+__device__ __forceinline__ void load8(const AT* row, int lane, float (&v)[8]) {
+  const float4 a = load4<AT>(row + 4 * lane);
+  const float4 b = load4<AT>(row + 128 + 4 * lane);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* row, int lane, const float (&v)[8]) {
+  store4<T>(row + 4 * lane, v[0], v[1], v[2], v[3]);
+  store4<T>(row + 128 + 4 * lane, v[4], v[5], v[6], v[7]);
+}
+
+// hh = modulate(LN(h), nsh1, nsc1)   (dmt.py:148)
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_node_ln1(Plan plan, const float* __restrict__ h, const float* __restrict__ ada, int l,
+                                                  AT* __restrict__ hh) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= plan.Mn) return;
+  const int mol = plan.node_info[m] >> 6;
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_NODE;
+  float v[8];
+  load8(h + static_cast<size_t>(m) * 256, lane, v);
+  ln256_mod<kFast>(v, ar + 0, ar + 256, lane);
+  store8<AT>(hh + static_cast<size_t>(m) * 256, lane, v);
+}
+
+// TransMixLayer (layers.py:131-186): one CTA per TARGET atom c; sources r != c of the same molecule.
+//   logits[r, 0:2]  = adjacency heads (1 or -1e10), logits[r, 2+h] = sum_d q[c,h,d] k[r,h,d] e0[(r,c),h,d] / 4
+//   alpha = softmax over r (max-subtracted, denominator + 1e-16);  hn[c, h, :] = sum_r alpha v[r,h,:] e1[(r,c),h,:]
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_attention(Plan plan, const float* __restrict__ qkv, const AT* __restrict__ e01,
+                                                   const uint8_t* __restrict__ pflags, float* __restrict__ hn,
+                                                   AT* __restrict__ hnb) {
+  __shared__ float sprod[16][QK_DIM + 1];
+  __shared__ float slog[MAX_ATOMS][N_HEADS];
+  __shared__ int srow[MAX_ATOMS];   // pair row of (c, r)
+  const int m = blockIdx.x;
+  const int t = threadIdx.x;
+  const uint32_t info = plan.node_info[m];
+  const int mol = info >> 6, c = info & 63;
+  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
+  if (t < n) srow[t] = (t == c) ? -1 : pbase + (t < c ? pair_index(n, t, c) : pair_index(n, c, t));
+  const float qc = (t < QK_DIM) ? qkv[static_cast<size_t>(m) * QKV_LD + t] : 0.f;
+  __syncthreads();
+
+  for (int r0 = 0; r0 < n; r0 += 16) {
+    if (t < QK_DIM) {
+#pragma unroll 4
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = r0 + rr;
+        float pr = 0.f;
+        if (r < n && r != c) {
+          const float kv = qkv[static_cast<size_t>(base + r) * QKV_LD + 256 + t];
+          const float ev = to_f32(e01[static_cast<size_t>(srow[r]) * E01_LD + t]);
+          pr = qc * kv * ev;
+        }
+        sprod[rr][t] = pr;
+      }
+    }
+    __syncthreads();
+    {
+      const int rr = t >> 4, hh = t & 15;
+      const int r = r0 + rr;
+      if (r < n && r != c) {
+        float lg;
+        if (hh < N_SUB) {
+          float s = 0.f;
+#pragma unroll
+          for (int d = 0; d < C_SUB; ++d) s += sprod[rr][hh * C_SUB + d];
+          lg = s * 0.25f;                       // 1/sqrt(out_channels = 16)
+          slog[r][2 + hh] = lg;
+        } else {
+          const int bit = hh - N_SUB;           // 0: adj2d, 1: adjsp
+          lg = ((pflags[srow[r]] >> bit) & 1) ? 1.0f : -1e10f;
+          slog[r][bit] = lg;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // softmax over sources, one warp per two heads
+  {
+    const int warp = t >> 5, lane = t & 31;
+#pragma unroll
+    for (int hsel = 0; hsel < 2; ++hsel) {
+      const int hh = warp * 2 + hsel;
+      float l0 = -INFINITY, l1 = -INFINITY;
+      const bool v0 = lane < n && lane != c, v1 = (lane + 32) < n && (lane + 32) != c;
+      if (v0) l0 = slog[lane][hh];
+      if (v1) l1 = slog[lane + 32][hh];
+      const float mx = warp_max(fmaxf(l0, l1));
+      const float e0 = v0 ? act_exp<kFast>(l0 - mx) : 0.f;
+      const float e1 = v1 ? act_exp<kFast>(l1 - mx) : 0.f;
+      const float den = warp_sum(e0 + e1) + 1e-16f;
+      if (v0) slog[lane][hh] = e0 / den;
+      if (v1) slog[lane + 32][hh] = e1 / den;
+    }
+  }
+  __syncthreads();
+
+  // messages: thread t <-> value channel t (head t/16)
+  float acc = 0.f;
+  const int hh = t >> 4;
+#pragma unroll 4
+  for (int r = 0; r < n; ++r) {
+    if (r == c) continue;
+    const float vv = qkv[static_cast<size_t>(base + r) * QKV_LD + 512 + t];
+    const float ev = to_f32(e01[static_cast<size_t>(srow[r]) * E01_LD + 256 + t]);
+    acc = fmaf(slog[r][hh] * vv, ev, acc);
+  }
+  hn[static_cast<size_t>(m) * 256 + t] = acc;
+  hnb[static_cast<size_t>(m) * 256 + t] = from_f32<AT>(acc);
+}
+
+// h1 = modulate(LN(h_in + ng1 * hn), nsh2, nsc2)   (dmt.py:159-161)
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_node_update1(Plan plan, const float* __restrict__ h, const float* __restrict__ hn,
+                                                      const float* __restrict__ ada, int l, float* __restrict__ h1,
+                                                      AT* __restrict__ h1b) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= plan.Mn) return;
+  const int mol = plan.node_info[m] >> 6;
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_NODE;
+  float v[8], a[8], g[8];
+  load8(h + static_cast<size_t>(m) * 256, lane, v);
+  load8(hn + static_cast<size_t>(m) * 256, lane, a);
+  load8(ar + 512, lane, g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = v[i] + g[i] * a[i];
+  ln256_mod<kFast>(v, ar + 768, ar + 1024, lane);
+  store8<float>(h1 + static_cast<size_t>(m) * 256, lane, v);
+  store8<AT>(h1b + static_cast<size_t>(m) * 256, lane, v);
+}
+
+// h = h1 + ng2 * FFN(h1)   (dmt.py:162-163)
+template <typename AT>
+__global__ void __launch_bounds__(256) k_node_update2(Plan plan, const float* __restrict__ h1, const float* __restrict__ f2,
+                                                      const float* __restrict__ ada, int l, float* __restrict__ h,
+                                                      AT* __restrict__ hb) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= plan.Mn) return;
+  const int mol = plan.node_info[m] >> 6;
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_NODE;
+  float v[8], a[8], g[8];
+  load8(h1 + static_cast<size_t>(m) * 256, lane, v);
+  load8(f2 + static_cast<size_t>(m) * 256, lane, a);
+  load8(ar + 1280, lane, g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = v[i] + g[i] * a[i];
+  store8<float>(h + static_cast<size_t>(m) * 256, lane, v);
+  store8<AT>(hb + static_cast<size_t>(m) * 256, lane, v);
+}
+
+// e1 = modulate(LN(e_in + eg1 * node2edge_lin(hn_i + hn_j)), esh2, esc2)   (dmt.py:156-157,165-167)
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_edge_update1(Plan plan, const float* __restrict__ e, const float* __restrict__ pn,
+                                                      const float* __restrict__ n2e_b, const float* __restrict__ ada, int l,
+                                                      float* __restrict__ e1f, AT* __restrict__ e1b) {
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= plan.Mp) return;
+  int mol, i, j;
+  unpack_pair(plan.pair_info[p], mol, i, j);
+  const int base = plan.noff[mol];
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_EDGE;
+  const float2 ev = *reinterpret_cast<const float2*>(e + static_cast<size_t>(p) * 64 + 2 * lane);
+  const float2 pi = *reinterpret_cast<const float2*>(pn + static_cast<size_t>(base + i) * 64 + 2 * lane);
+  const float2 pj = *reinterpret_cast<const float2*>(pn + static_cast<size_t>(base + j) * 64 + 2 * lane);
+  const float2 bb = *reinterpret_cast<const float2*>(n2e_b + 2 * lane);
+  const float2 g = *reinterpret_cast<const float2*>(ar + 128 + 2 * lane);
+  float v0 = ev.x + g.x * ((pi.x + pj.x) + bb.x);
+  float v1 = ev.y + g.y * ((pi.y + pj.y) + bb.y);
+  ln64_mod<kFast>(v0, v1, ar + 192, ar + 256, lane);
+  store2<float>(e1f + static_cast<size_t>(p) * 64 + 2 * lane, v0, v1);
+  store2<AT>(e1b + static_cast<size_t>(p) * 64 + 2 * lane, v0, v1);
+}
+
+// e = e1 + eg2 * FFN(e1)  (dmt.py:168-169); also refreshes the [dist | e] GEMM operand
+template <typename AT>
+__global__ void __launch_bounds__(256) k_edge_update2(Plan plan, const float* __restrict__ e1f, const float* __restrict__ f4,
+                                                      const float* __restrict__ ada, int l, float* __restrict__ e,
+                                                      AT* __restrict__ X) {
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= plan.Mp) return;
+  const int mol = plan.pair_info[p] >> 12;
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_EDGE;
+  const float2 a = *reinterpret_cast<const float2*>(e1f + static_cast<size_t>(p) * 64 + 2 * lane);
+  const float2 f = *reinterpret_cast<const float2*>(f4 + static_cast<size_t>(p) * 64 + 2 * lane);
+  const float2 g = *reinterpret_cast<const float2*>(ar + 320 + 2 * lane);
+  const float v0 = a.x + g.x * f.x, v1 = a.y + g.y * f.y;
+  store2<float>(e + static_cast<size_t>(p) * 64 + 2 * lane, v0, v1);
+  store2<AT>(X + static_cast<size_t>(p) * 128 + 64 + 2 * lane, v0, v1);
+}
+
+// Z[d] = modulate(LN(input_lin([h_r | h_c | e | dist])), csh, csc) for the directed edge d = 2p + dir:
+// dir 0 -> (r=i, c=j), dir 1 -> (r=j, c=i)    (dmt.py:39-44)
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const float* __restrict__ ab, const AT* __restrict__ gp,
+                                                  const float* __restrict__ ada, int l, AT* __restrict__ Z) {
+  const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (d >= 2 * plan.Mp) return;
+  const int p = d >> 1;
+  int mol, i, j;
+  unpack_pair(plan.pair_info[p], mol, i, j);
+  const int base = plan.noff[mol];
+  const int r = (d & 1) ? j : i, c = (d & 1) ? i : j;
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_COORD;
+  float v[8], a[8], g[8];
+  load8(ab + static_cast<size_t>(base + r) * 512, lane, v);
+  load8(ab + static_cast<size_t>(base + c) * 512 + 256, lane, a);
+  load8<AT>(gp + static_cast<size_t>(p) * 256, lane, g);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = (v[k] + a[k]) + g[k];
+  ln256_mod<kFast>(v, ar + 0, ar + 256, lane);
+  store8<AT>(Z + static_cast<size_t>(d) * 256, lane, v);
+}
+
+// w[d] = mean(tanh(coord_mlp.2(u1[d])) * [1, adj2d, adjsp])   (dmt.py:46-51)
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_coord_out(Plan plan, const AT* __restrict__ u1, const float* __restrict__ wc2,
+                                                   const uint8_t* __restrict__ pflags, float* __restrict__ wdir) {
+  const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (d >= 2 * plan.Mp) return;
+  float v[8];
+  load8<AT>(u1 + static_cast<size_t>(d) * 256, lane, v);
+  float s[3];
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    float w[8];
+    load8(wc2 + o * 256, lane, w);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fmaf(v[k], w[k], acc);
+    s[o] = act_tanh<kFast>(warp_sum(acc));
+  }
+  if (lane == 0) {
+    const uint8_t f = pflags[d >> 1];
+    const float a2 = (f & 1) ? 1.f : 0.f, asp = (f & 2) ? 1.f : 0.f;
+    wdir[d] = (s[0] + s[1] * a2 + s[2] * asp) / 3.0f;
+  }
+}
+
+// pos_r += sum_c (pos_r - pos_c)/max(|.|,1e-8) * scale * w[r,c]; then centre-of-mass removal
+// (dmt.py:40-41,53-58, layers.py:344-347, dmt.py:385-386)
+__global__ void __launch_bounds__(64) k_pos_update(Plan plan, const float* __restrict__ wdir, const float* __restrict__ scale_p,
+                                                   float* __restrict__ pos) {
+  __shared__ float sp[MAX_ATOMS][3];
+  __shared__ float red[3][2];
+  const int mol = blockIdx.x, r = threadIdx.x;
+  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
+  if (r < n) {
+    sp[r][0] = pos[(base + r) * 3 + 0];
+    sp[r][1] = pos[(base + r) * 3 + 1];
+    sp[r][2] = pos[(base + r) * 3 + 2];
+  }
+  __syncthreads();
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  if (r < n) {
+    const float scale = scale_p[0];
+    const float px = sp[r][0], py = sp[r][1], pz = sp[r][2];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int c = 0; c < n; ++c) {
+      if (c == r) continue;
+      const float dx = px - sp[c][0], dy = py - sp[c][1], dz = pz - sp[c][2];
+      const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
+      const int d = (r < c) ? 2 * (pbase + pair_index(n, r, c)) : 2 * (pbase + pair_index(n, c, r)) + 1;
+      const float w = wdir[d];
+      ax += (dx / nrm * scale) * w;
+      ay += (dy / nrm * scale) * w;
+      az += (dz / nrm * scale) * w;
+    }
+    nx = px + ax; ny = py + ay; nz = pz + az;
+  }
+  const float sx = warp_sum(nx), sy = warp_sum(ny), sz = warp_sum(nz);
+  if ((r & 31) == 0) { red[0][r >> 5] = sx; red[1][r >> 5] = sy; red[2][r >> 5] = sz; }
+  __syncthreads();
+  if (r < n) {
+    const float fn = static_cast<float>(n);
+    pos[(base + r) * 3 + 0] = nx - (red[0][0] + red[0][1]) / fn;
+    pos[(base + r) * 3 + 1] = ny - (red[1][0] + red[1][1]) / fn;
+    pos[(base + r) * 3 + 2] = nz - (red[2][0] + red[2][1]) / fn;
+  }
+}
+
+// ----------------------------------------------------------------------------- heads
+// atom_pred = node_pred_mlp.4(n2)   (dmt.py:391-393)
+template <typename AT>
+__global__ void __launch_bounds__(256) k_node_head_out(Plan plan, const AT* __restrict__ n2, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float* __restrict__ pred) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= plan.Mn) return;
+  const float4 v = load4<AT>(n2 + static_cast<size_t>(m) * 128 + 4 * lane);
+#pragma unroll
+  for (int o = 0; o < 6; ++o) {
+    const float4 ww = *reinterpret_cast<const float4*>(w + o * 128 + 4 * lane);
+    const float s = warp_sum(v.x * ww.x + v.y * ww.y + v.z * ww.z + v.w * ww.w);
+    if (lane == 0) pred[static_cast<size_t>(m) * 9 + 3 + o] = s + b[o];
+  }
+}
+
+// edge_pred = [edge_exist_mlp, edge_type_mlp] layers 2 and 4 (dmt.py:394); layer 0 (both heads) is the GEMM eh1
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_edge_head_out(Plan plan, const AT* __restrict__ eh1, const float* __restrict__ w2t,
+                                                       const float* __restrict__ b2, const float* __restrict__ w4,
+                                                       const float* __restrict__ b4, float* __restrict__ pred_e) {
+  __shared__ float row[8][128];
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 8 + wi;
+  if (p >= plan.Mp) return;
+  const float4 v = load4<AT>(eh1 + static_cast<size_t>(p) * 128 + 4 * lane);
+  row[wi][4 * lane + 0] = v.x; row[wi][4 * lane + 1] = v.y; row[wi][4 * lane + 2] = v.z; row[wi][4 * lane + 3] = v.w;
+  __syncwarp();
+#pragma unroll
+  for (int hd = 0; hd < 2; ++hd) {
+    float acc = b2[hd * 32 + lane];
+    const float* wt = w2t + hd * 64 * 32;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) acc = fmaf(wt[k * 32 + lane], row[wi][hd * 64 + k], acc);
+    const float s = warp_sum(act_silu<kFast>(acc) * w4[hd * 32 + lane]);
+    if (lane == 0) pred_e[static_cast<size_t>(p) * 2 + hd] = s + b4[hd];
+  }
+}
+
+// NaN guard (dmt.py:407-409) is batch-global: first detect, then zero / re-centre (dmt.py:402-412)
+__global__ void k_pos_nan_flag(int Mn, const float* __restrict__ pos, int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool bad = (i < Mn * 3) && isnan(pos[i]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&flags[1], 1);
+}
+__global__ void __launch_bounds__(64) k_pos_final(Plan plan, const float* __restrict__ pos, const int* __restrict__ flags,
+                                                  float* __restrict__ pred) {
+  __shared__ float red[3][2];
+  const int mol = blockIdx.x, r = threadIdx.x;
+  const int n = plan.n_atoms[mol], base = plan.noff[mol];
+  const bool zero = flags[1] != 0;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (r < n && !zero) {
+    x = pos[(base + r) * 3 + 0]; y = pos[(base + r) * 3 + 1]; z = pos[(base + r) * 3 + 2];
+  }
+  const float sx = warp_sum(x), sy = warp_sum(y), sz = warp_sum(z);
+  if ((r & 31) == 0) { red[0][r >> 5] = sx; red[1][r >> 5] = sy; red[2][r >> 5] = sz; }
+  __syncthreads();
+  if (r < n) {
+    const float fn = static_cast<float>(n);
+    pred[static_cast<size_t>(base + r) * 9 + 0] = x - (red[0][0] + red[0][1]) / fn;
+    pred[static_cast<size_t>(base + r) * 9 + 1] = y - (red[1][0] + red[1][1]) / fn;
+    pred[static_cast<size_t>(base + r) * 9 + 2] = z - (red[2][0] + red[2][1]) / fn;
+  }
+}
+
+__global__ void k_zero_flags(int* flags) {
+  if (threadIdx.x < 4) flags[threadIdx.x] = 0;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+#define LAUNCH_CHECK(ctx)                     \
+  do {                                        \
+    DS_CUDA_CHECK(cudaGetLastError());        \
+    (ctx)->launch_count++;                    \
+  } while (0)
+
+template <typename AT, bool kFast>
+int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, const float* xs, const float* es,
+                 const float* cond_x, const float* cond_e, const float* noise_level, StepRef sr, const float* ctx_emb,
+                 float* pred_x, float* pred_e, DenoiseWs& w, cudaStream_t s) {
+  const int B = plan.B, Mn = plan.Mn, Mp = plan.Mp, Md = 2 * plan.Mp;
+  const int AD = kFast ? DT_BF16 : DT_F32;
+  AT* X = reinterpret_cast<AT*>(w.X);
+
+  k_zero_flags<<<1, 32, 0, s>>>(w.flags);
+  LAUNCH_CHECK(ctx);
+  // time embedding (+ cached spectral context) -> SiLU -> per-molecule adaLN table
+  k_time_feat<AT><<<B, 256, 0, s>>>(noise_level, sr, pw.tm_freq, pw.tm1_w, pw.tm1_b, reinterpret_cast<AT*>(w.tfeat));
+  LAUNCH_CHECK(ctx);
+  DS_TRY(linear(ctx, w.tfeat, D_TIME, pw.tm3_w, D_TIME, pw.tm3_b, ctx_emb, D_TIME, w.s_act, D_TIME, AD, B, D_TIME, D_TIME,
+                ACT_SILU, s));
+  DS_TRY(linear(ctx, w.s_act, D_TIME, pw.w_ada, D_TIME, pw.b_ada, nullptr, 0, w.ada, ADA_LD, DT_F32, B, ADA_LD, D_TIME,
+                ACT_NONE, s));
+  // root embeddings
+  k_root_nodes<AT><<<Mn, 256, 0, s>>>(Mn, xs, cond_x, pw.node_emb_w, pw.node_emb_b, w.h, reinterpret_cast<AT*>(w.hb),
+                                      reinterpret_cast<AT*>(w.ahid), w.pos);
+  LAUNCH_CHECK(ctx);
+  if (Mp > 0) {
+    k_root_pair_flags<<<cdiv(Mp, 256), 256, 0, s>>>(plan, cond_x, cond_e, w.pflags, w.flags);
+    LAUNCH_CHECK(ctx);
+    k_root_pairs<AT, kFast><<<cdiv(Mp, 4), 256, 0, s>>>(plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means,
+                                                        pw.root_stds, pw.edge_emb_w, pw.edge_emb_b, w.e, X,
+                                                        reinterpret_cast<AT*>(w.ehid));
+    LAUNCH_CHECK(ctx);
+  }
+
+  for (int l = 0; l < N_LAYERS; ++l) {
+    const BlockWeights& bw = pw.blk[l];
+    if (Mp > 0) {
+      k_rbf<AT, kFast><<<cdiv(Mp, 4), 256, 0, s>>>(plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
+      LAUNCH_CHECK(ctx);
+      DS_TRY(linear(ctx, X, 128, bw.edge_emb_w, 128, bw.edge_emb_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
+      k_pair_ln1<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.y1, w.ada, l, reinterpret_cast<AT*>(w.ea));
+      LAUNCH_CHECK(ctx);
+      DS_TRY(linear(ctx, w.ea, 64, bw.w01, 64, nullptr, nullptr, 0, w.e01, E01_LD, AD, Mp, E01_LD, 64, ACT_TANH, s));
+    }
+    k_node_ln1<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h, w.ada, l, reinterpret_cast<AT*>(w.hh));
+    LAUNCH_CHECK(ctx);
+    DS_TRY(linear(ctx, w.hh, 256, bw.wqkv, 256, bw.bqkv, nullptr, 0, w.qkv, QKV_LD, DT_F32, Mn, QKV_LD, 256, ACT_NONE, s));
+    k_attention<AT, kFast><<<Mn, 256, 0, s>>>(plan, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags, w.hn,
+                                              reinterpret_cast<AT*>(w.hnb));
+    LAUNCH_CHECK(ctx);
+    DS_TRY(linear(ctx, w.hnb, 256, bw.n2e_w, 256, nullptr, nullptr, 0, w.pn, 64, DT_F32, Mn, 64, 256, ACT_NONE, s));
+    // node stream
+    k_node_update1<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h, w.hn, w.ada, l, w.h1, reinterpret_cast<AT*>(w.h1b));
+    LAUNCH_CHECK(ctx);
+    DS_TRY(linear(ctx, w.h1b, 256, bw.ff1_w, 256, bw.ff1_b, nullptr, 0, w.f1, 512, AD, Mn, 512, 256, ACT_SILU, s));
+    DS_TRY(linear(ctx, w.f1, 512, bw.ff2_w, 512, bw.ff2_b, nullptr, 0, w.f2, 256, DT_F32, Mn, 256, 512, ACT_NONE, s));
+    k_node_update2<AT><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h1, w.f2, w.ada, l, w.h, reinterpret_cast<AT*>(w.hb));
+    LAUNCH_CHECK(ctx);
+    if (Mp > 0) {
+      // edge stream
+      k_edge_update1<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
+                                                            reinterpret_cast<AT*>(w.e1b));
+      LAUNCH_CHECK(ctx);
+      DS_TRY(linear(ctx, w.e1b, 64, bw.ff3_w, 64, bw.ff3_b, nullptr, 0, w.f3, 128, AD, Mp, 128, 64, ACT_SILU, s));
+      DS_TRY(linear(ctx, w.f3, 128, bw.ff4_w, 128, bw.ff4_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
+      k_edge_update2<AT><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.e1f, w.y1, w.ada, l, w.e, X);
+      LAUNCH_CHECK(ctx);
+      // equivariant coordinate update
+      DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, s));
+      DS_TRY(linear(ctx, w.hb, 256, bw.wab, 256, bw.bab, nullptr, 0, w.ab, 512, DT_F32, Mn, 512, 256, ACT_NONE, s));
+      k_coord_ln<AT, kFast><<<cdiv(Md, 8), 256, 0, s>>>(plan, w.ab, reinterpret_cast<const AT*>(w.gp), w.ada, l,
+                                                        reinterpret_cast<AT*>(w.Z));
+      LAUNCH_CHECK(ctx);
+      DS_TRY(linear(ctx, w.Z, 256, bw.wc1, 256, bw.bc1, nullptr, 0, w.u1, 256, AD, Md, 256, 256, ACT_SILU, s));
+      k_coord_out<AT, kFast><<<cdiv(Md, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.u1), bw.wc2, w.pflags, w.wdir);
+      LAUNCH_CHECK(ctx);
+    }
+    k_pos_update<<<B, 64, 0, s>>>(plan, w.wdir, bw.coord_scale, w.pos);
+    LAUNCH_CHECK(ctx);
+    // skip connections into the prediction heads (dmt.py:387-388)
+    DS_TRY(linear(ctx, w.hb, 256, bw.node_w, 256, bw.node_b, nullptr, 0, reinterpret_cast<AT*>(w.ahid) + 256 + 64 * l, 768,
+                  AD, Mn, 64, 256, ACT_NONE, s));
+    if (Mp > 0)
+      DS_TRY(linear(ctx, X + 64, 128, bw.edge_w, 64, bw.edge_b, nullptr, 0, reinterpret_cast<AT*>(w.ehid) + 64 + 16 * l,
+                    192, AD, Mp, 16, 64, ACT_NONE, s));
+  }
+
+  // prediction heads (dmt.py:391-399)
+  DS_TRY(linear(ctx, w.ahid, 768, pw.np0_w, 768, pw.np0_b, nullptr, 0, w.n1, 256, AD, Mn, 256, 768, ACT_SILU, s));
+  DS_TRY(linear(ctx, w.n1, 256, pw.np2_w, 256, pw.np2_b, nullptr, 0, w.n2, 128, AD, Mn, 128, 256, ACT_SILU, s));
+  k_node_head_out<AT><<<cdiv(Mn, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.n2), pw.np4_w, pw.np4_b, pred_x);
+  LAUNCH_CHECK(ctx);
+  if (Mp > 0) {
+    DS_TRY(linear(ctx, w.ehid, 192, pw.eh0_w, 192, pw.eh0_b, nullptr, 0, w.eh1, 128, AD, Mp, 128, 192, ACT_SILU, s));
+    k_edge_head_out<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.eh1), pw.eh2t_w, pw.eh2_b,
+                                                           pw.eh4_w, pw.eh4_b, pred_e);
+    LAUNCH_CHECK(ctx);
+  }
+  k_pos_nan_flag<<<cdiv(Mn * 3, 256), 256, 0, s>>>(Mn, w.pos, w.flags);
+  LAUNCH_CHECK(ctx);
+  k_pos_final<<<B, 64, 0, s>>>(plan, w.pos, w.flags, pred_x);
+  LAUNCH_CHECK(ctx);
+  return DS_OK;
+}
+
+}  // namespace
+
+int linear(DsContext* ctx, const void* A, int lda, const void* W, int ldw, const float* bias, const float* addmat,
+           int ldadd, void* out, int ldo, int out_dtype, int M, int N, int K, int act, cudaStream_t s) {
+  if (M <= 0) return DS_OK;
+  GemmDesc g;
+  g.A = A; g.W = W; g.bias = bias; g.addmat = addmat; g.out = out;
+  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldadd = ldadd;
+  g.a_dtype = ds_is_bf16(ctx) ? DT_BF16 : DT_F32;
+  g.out_dtype = out_dtype;
+  g.act = act;
+  if (ds_is_bf16(ctx) && (K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && N >= 8) return gemm_tc_launch(ctx, g, s);
+  ctx->launch_count++;
+  return gemm_simt_launch(g, ds_is_bf16(ctx), s);
+}
+
+size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf) {
+  const size_t es = bf ? 2 : 4;
+  const size_t mn = Mn > 0 ? Mn : 1, mp = Mp > 0 ? Mp : 1, md = 2 * mp, b = B;
+  const size_t start = a.off;
+  w.tfeat_f = nullptr;
+  w.tfeat = a.take(b * D_TIME * es);
+  w.s_act = a.take(b * D_TIME * es);
+  w.ada = static_cast<float*>(a.take(b * ADA_LD * 4));
+  w.h = static_cast<float*>(a.take(mn * 256 * 4));
+  w.hb = a.take(mn * 256 * es);
+  w.h1 = static_cast<float*>(a.take(mn * 256 * 4));
+  w.h1b = a.take(mn * 256 * es);
+  w.pos = static_cast<float*>(a.take(mn * 3 * 4));
+  w.hh = a.take(mn * 256 * es);
+  w.qkv = static_cast<float*>(a.take(mn * QKV_LD * 4));
+  w.hn = static_cast<float*>(a.take(mn * 256 * 4));
+  w.hnb = a.take(mn * 256 * es);
+  w.pn = static_cast<float*>(a.take(mn * 64 * 4));
+  w.f1 = a.take(mn * 512 * es);
+  w.f2 = static_cast<float*>(a.take(mn * 256 * 4));
+  w.ab = static_cast<float*>(a.take(mn * 512 * 4));
+  w.ahid = a.take(mn * 768 * es);
+  w.n1 = a.take(mn * 256 * es);
+  w.n2 = a.take(mn * 128 * es);
+  w.e = static_cast<float*>(a.take(mp * 64 * 4));
+  w.e1f = static_cast<float*>(a.take(mp * 64 * 4));
+  w.e1b = a.take(mp * 64 * es);
+  w.X = a.take(mp * 128 * es);
+  w.y1 = static_cast<float*>(a.take(mp * 64 * 4));
+  w.ea = a.take(mp * 64 * es);
+  w.e01 = a.take(mp * E01_LD * es);
+  w.f3 = a.take(mp * 128 * es);
+  w.gp = a.take(mp * 256 * es);
+  w.ehid = a.take(mp * 192 * es);
+  w.eh1 = a.take(mp * 128 * es);
+  w.pflags = static_cast<uint8_t*>(a.take(mp));
+  w.Z = a.take(md * 256 * es);
+  w.u1 = a.take(md * 256 * es);
+  w.wdir = static_cast<float*>(a.take(md * 4));
+  w.flags = static_cast<int*>(a.take(16));
+  return a.off - start;
+}
+
+int denoise_packed(DsContext* ctx, const PackedWeights& pw, const Plan& plan, const float* xs, const float* es,
+                   const float* cond_x, const float* cond_e, const float* noise_level, StepRef sr, const float* ctx_emb,
+                   float* pred_x, float* pred_e, DenoiseWs& w, cudaStream_t s) {
+  DS_CHECK(pw.valid, DS_ERR_INVALID, "denoise: weights not packed (call ds_pack_weights first)");
+  DS_CHECK(plan.Mn > 0, DS_ERR_INVALID, "denoise: empty plan");
+  DS_CHECK((cond_x == nullptr) == (cond_e == nullptr), DS_ERR_INVALID, "denoise: cond_x and cond_edge_x must both be given or both null");
+  if (ds_is_bf16(ctx))
+    return denoise_impl<bf16, true>(ctx, pw, plan, xs, es, cond_x, cond_e, noise_level, sr, ctx_emb, pred_x, pred_e, w, s);
+  return denoise_impl<float, false>(ctx, pw, plan, xs, es, cond_x, cond_e, noise_level, sr, ctx_emb, pred_x, pred_e, w, s);
+}

@@ -152,6 +152,8 @@ struct NoiseSrc {
   const float* raw_e;     // [steps][B,2,N,N]
   unsigned long long seed;      // Philox key when raw_* are null
   long long gid_base;           // global id of molecule 0 of this shard (sharding-invariant noise)
+  int philox_step_offset;       // added to the step index for the Philox counter (stand-alone sampler step)
+  int raw_step_base;            // raw_* arrays start at this step (segmented loop)
 };
 int launch_sampler_step(DsContext* ctx, const Plan& plan, float* xs, float* es, const float* pred_x,
                         const float* pred_e, float* xmean, float* emean, StepRef sr, int step_host,

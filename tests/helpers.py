@@ -1,0 +1,36 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import torch
+
+from oracle import weights as W
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
+
+
+def max_abs(a, b):
+    return (a.double().cpu() - b.double().cpu()).abs().max().item()
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def keyed_state_dict(module, salt=0, coord_scale=None):
+    sd = module.state_dict()
+    W.keyed_fill_(sd, salt=salt, coord_scale=coord_scale)
+    module.load_state_dict(sd)
+    return sd
+
+
+def build_model(version, salt=0, coord_scale=None, precision='fp32', device='cuda'):
+    from diffspectra_b200.config import get_config
+    from diffspectra_b200.model import DMT_B200
+    m = DMT_B200(get_config(version, device=device, precision=precision)).eval()
+    keyed_state_dict(m, salt, coord_scale)
+    return m.to(device)
