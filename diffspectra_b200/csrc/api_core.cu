@@ -54,6 +54,7 @@ int ds_destroy(ds_ctx* h) {
   DsContext* c = reinterpret_cast<DsContext*>(h);
   if (!c) return DS_OK;
   if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+  if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
   ds_ctx_free(c);
   return DS_OK;
 }

@@ -267,9 +267,14 @@ int ds_sample_loop(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp
       }
       const long long before = c->launch_count;
       cudaGraph_t graph = nullptr;
+      // The legacy default stream cannot be captured: record the step on a private stream, replay on the caller's.
+      if (c->capture_stream == nullptr) DS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
+      cudaStream_t user_stream = s;
+      s = c->capture_stream;
       DS_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       int r = one_step();
       cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      s = user_stream;
       if (r != DS_OK) {
         if (graph) cudaGraphDestroy(graph);
         return r;

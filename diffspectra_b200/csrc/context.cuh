@@ -17,6 +17,7 @@ struct DsContext {
   long long launch_count = 0;        // kernels launched (or captured) through this context
   // cached CUDA graph of one sampling step (ds_sample_loop)
   cudaGraphExec_t step_graph = nullptr;
+  cudaStream_t capture_stream = nullptr;
   long long step_graph_launches = 0;   // kernels inside one replay of step_graph
 };
 
