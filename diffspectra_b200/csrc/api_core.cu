@@ -1,5 +1,6 @@
 // C-ABI entry points: context lifetime, error reporting and the GEMM test hook.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/diffspectra_b200.h"
 #include "context.cuh"
@@ -41,6 +42,7 @@ int ds_create(ds_ctx** out, int device, int mode, int spectra_version) {
   c->mode = mode;
   c->spectra_version = spectra_version;
   c->num_sms = prop.multiProcessorCount;
+  if (const char* fm = getenv("DS_FUSE_MASK")) c->fuse_mask = atoi(fm);
   int r = gemm_tc_init(c);
   if (r != DS_OK) {
     ds_ctx_free(c);
@@ -74,6 +76,22 @@ int ds_gemm(ds_ctx* h, int use_tensor_cores, const void* A, int lda, const void*
   if (use_tensor_cores) return gemm_tc_launch(c, g, s);
   c->launch_count++;
   return gemm_simt_launch(g, c->mode == 1, s);
+}
+
+int ds_gemm_fused(ds_ctx* h, int mode, const void* A, int lda, const void* W, int ldw, const float* bias, int M, int N, int K,
+                  const unsigned* row_info, int info_shift, const float* ada, int off_a, int off_b, const float* resid,
+                  int ldres, void* out, int ldo, void* out2, int ldo2, const float* wc2, const unsigned char* dflags,
+                  float* wdir, void* stream) {
+  DsContext* c = reinterpret_cast<DsContext*>(h);
+  DS_CHECK(c != nullptr, DS_ERR_INVALID, "ds_gemm_fused: null ctx");
+  GemmDesc g;
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.M = M; g.N = N; g.K = K;
+  g.a_dtype = DT_BF16; g.mode = mode;
+  g.out_dtype = (mode == GEMM_LNMOD) ? DT_BF16 : DT_F32;
+  g.row_info = row_info; g.info_shift = info_shift; g.ada = ada; g.off_a = off_a; g.off_b = off_b;
+  g.resid = resid; g.ldres = ldres; g.out = out; g.ldo = ldo; g.out2 = out2; g.ldo2 = ldo2;
+  g.wc2 = wc2; g.pflags = dflags; g.wdir = wdir;
+  return gemm_tc_launch(c, g, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -143,16 +143,31 @@ __device__ __forceinline__ int pair_index(int n, int i, int j) {   // i < j < n,
 }
 
 // ----------------------------------------------------------------------------- GEMM  out = act(A W^T + bias + addmat)
+enum GemmMode { GEMM_STORE = 0, GEMM_LNMOD = 1, GEMM_RESGATE = 2, GEMM_COORD = 3 };
+
 struct GemmDesc {
-  const void* A;      // [M, K] row-major, leading dim lda (elements); dtype a_dtype
-  const void* W;      // [N, K] row-major, leading dim ldw; same dtype as A
-  const float* bias;  // [N] or null
-  const float* addmat;   // [M, ldadd] fp32 added before the activation, or null
-  void* out;          // [M, N] row-major, leading dim ldo; dtype out_dtype
-  int M, N, K;
-  int lda, ldw, ldo, ldadd;
-  int a_dtype, out_dtype;
-  int act;
+  const void* A = nullptr;      // [M, K] row-major, leading dim lda (elements); dtype a_dtype
+  const void* W = nullptr;      // [N, K] row-major, leading dim ldw; same dtype as A
+  const float* bias = nullptr;  // [N] or null
+  const float* addmat = nullptr;   // [M, ldadd] fp32 added before the activation, or null
+  void* out = nullptr;          // [M, N] row-major, leading dim ldo; dtype out_dtype
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldw = 0, ldo = 0, ldadd = 0;
+  int a_dtype = DT_F32, out_dtype = DT_F32;
+  int act = ACT_NONE;
+  // fused epilogues of the tcgen05 kernel (gemm_tc.cu)
+  int mode = GEMM_STORE;
+  const uint32_t* row_info = nullptr;   // row -> molecule: row_info[row] >> info_shift
+  int info_shift = 0;
+  const float* ada = nullptr;           // adaLN table pre-offset to the block; row stride ADA_LD
+  int off_a = 0, off_b = 0;             // LNMOD: shift / scale offsets; RESGATE: gate offset
+  const float* resid = nullptr;         // RESGATE residual stream [M, ldres] fp32
+  int ldres = 0;
+  void* out2 = nullptr;                 // RESGATE bf16 copy [M, ldo2]
+  int ldo2 = 0;
+  const float* wc2 = nullptr;           // COORD: coord_mlp.2 [3,256]
+  const uint8_t* pflags = nullptr;      // COORD: adjacency bits per pair
+  float* wdir = nullptr;                // COORD: output per directed edge
 };
 
 struct DsContext;

@@ -113,7 +113,7 @@ __global__ void k_root_pair_flags(Plan plan, const float* __restrict__ cond, con
   if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(&flags[0], 1);
 }
 
-// e = edge_emb([edge_x(2) | cond_edge(2) | RBF_root(r0)(64)])   (dmt.py:363-377)
+// e = edge_emb([edge_x(2) | cond_edge(2) | RBF_root(r0)(64)])   (dmt.py:363-377); 32 pairs per block
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_root_pairs(Plan plan, const float* __restrict__ es, const float* __restrict__ cond,
                                                     const float* __restrict__ cond_e, const float* __restrict__ ada,
@@ -121,17 +121,20 @@ __global__ void __launch_bounds__(256) k_root_pairs(Plan plan, const float* __re
                                                     const float* __restrict__ stds, const float* __restrict__ w,
                                                     const float* __restrict__ b, float* __restrict__ e,
                                                     AT* __restrict__ X, AT* __restrict__ ehid) {
-  __shared__ float in[4][68];
-  const int pl = threadIdx.x >> 6, k = threadIdx.x & 63;
-  const int p = blockIdx.x * 4 + pl;
-  const bool valid = p < plan.Mp;
-  if (valid) {
+  __shared__ float in[32][69];
+  __shared__ float wt[68][64];     // transposed edge_emb weight
+  for (int idx = threadIdx.x; idx < 64 * 68; idx += 256) wt[idx % 68][idx / 68] = w[idx];
+  const bool any = flags[0] != 0;
+  for (int idx = threadIdx.x; idx < 32 * 64; idx += 256) {
+    const int pl = idx >> 6, k = idx & 63;
+    const int p = blockIdx.x * 32 + pl;
+    if (p >= plan.Mp) continue;
     int mol, i, j;
     unpack_pair(plan.pair_info[p], mol, i, j);
     if (k < 2) in[pl][k] = es[p * 2 + k];
     else if (k < 4) in[pl][k] = cond_e ? cond_e[p * 2 + (k - 2)] : 0.f;
     float d0 = 0.f;
-    if (flags[0] != 0) {
+    if (any) {
       const int base = plan.noff[mol];
       const float* ci = cond + static_cast<size_t>(base + i) * 9;
       const float* cj = cond + static_cast<size_t>(base + j) * 9;
@@ -144,22 +147,30 @@ __global__ void __launch_bounds__(256) k_root_pairs(Plan plan, const float* __re
     in[pl][4 + k] = d0;
   }
   __syncthreads();
-  if (!valid) return;
-  float acc = b[k];
+  for (int idx = threadIdx.x; idx < 32 * 64; idx += 256) {
+    const int pl = idx >> 6, k = idx & 63;
+    const int p = blockIdx.x * 32 + pl;
+    if (p >= plan.Mp) continue;
+    float acc = b[k];
 #pragma unroll 4
-  for (int c = 0; c < 68; ++c) acc = fmaf(w[k * 68 + c], in[pl][c], acc);
-  e[static_cast<size_t>(p) * D_EDGE + k] = acc;
-  X[static_cast<size_t>(p) * 128 + 64 + k] = from_f32<AT>(acc);
-  ehid[static_cast<size_t>(p) * 192 + k] = from_f32<AT>(acc);
+    for (int c = 0; c < 68; ++c) acc = fmaf(wt[c][k], in[pl][c], acc);
+    e[static_cast<size_t>(p) * D_EDGE + k] = acc;
+    X[static_cast<size_t>(p) * 128 + 64 + k] = from_f32<AT>(acc);
+    ehid[static_cast<size_t>(p) * 192 + k] = from_f32<AT>(acc);
+  }
 }
 
 // ----------------------------------------------------------------------------- per-block kernels
-// X[:, 0:64] = RBF_l(|pos_i - pos_j|^2)   (dmt.py:136-138)
+template <typename AT>
+__device__ __forceinline__ void store2(AT* p, float a, float b);
+template <typename AT>
+__device__ __forceinline__ void store4(AT* p, float a, float b, float c, float d);
+// X[:, 0:64] = RBF_l(|pos_i - pos_j|^2)   (dmt.py:136-138); 8 threads per pair, 8 channels each
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict__ pos, const float* __restrict__ ada, int l,
                                              const float* __restrict__ means, const float* __restrict__ stds,
                                              AT* __restrict__ X) {
-  const int p = blockIdx.x * 4 + (threadIdx.x >> 6), k = threadIdx.x & 63;
+  const int p = blockIdx.x * 32 + (threadIdx.x >> 3), k0 = (threadIdx.x & 7) * 8;
   if (p >= plan.Mp) return;
   int mol, i, j;
   unpack_pair(plan.pair_info[p], mol, i, j);
@@ -170,7 +181,12 @@ __global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict_
   const float r2 = dx * dx + dy * dy + dz * dz;
   const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_RBF;
   const float x = r2 * (ar[0] + 1.0f) + ar[1];
-  X[static_cast<size_t>(p) * 128 + k] = from_f32<AT>(rbf_value<kFast>(x, k, means, stds));
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = rbf_value<kFast>(x, k0 + k, means, stds);
+  AT* o = X + static_cast<size_t>(p) * 128 + k0;
+  store4<AT>(o, v[0], v[1], v[2], v[3]);
+  store4<AT>(o + 4, v[4], v[5], v[6], v[7]);
 }
 
 // 64-wide LayerNorm + modulate, one warp per row, lane owns channels (2*lane, 2*lane+1)
@@ -376,6 +392,100 @@ __global__ void __launch_bounds__(256) k_attention(Plan plan, const float* __res
   hnb[static_cast<size_t>(m) * 256 + t] = from_f32<AT>(acc);
 }
 
+// TransMixLayer, one CTA per MOLECULE (n <= 32): q/k/v of the molecule live in shared memory, every pair row of
+// e0|e1 is streamed once per pass and serves both directions (i->j and j->i), logits / softmax weights stay in
+// shared memory, messages are accumulated per value channel without atomics.
+constexpr int ATT_MOL_MAXN = 32;
+__host__ __device__ inline size_t att_mol_smem_bytes(int n) {
+  return (static_cast<size_t>(n) * QKV_LD + static_cast<size_t>(n) * n * N_HEADS + static_cast<size_t>(n) * 256) * 4;
+}
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_attention_mol(Plan plan, const float* __restrict__ qkv, const AT* __restrict__ e01,
+                                                       const uint8_t* __restrict__ pflags, float* __restrict__ hn,
+                                                       AT* __restrict__ hnb) {
+  extern __shared__ float att_smem[];
+  const int mol = blockIdx.x, t = threadIdx.x;
+  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
+  const int npairs = n * (n - 1) / 2;
+  float* sq = att_smem;                                   // [n][768]
+  float* slog = sq + static_cast<size_t>(n) * QKV_LD;     // [tgt][src][16]
+  float* shn = slog + static_cast<size_t>(n) * n * N_HEADS;   // [n][256]
+  {
+    const float4* src = reinterpret_cast<const float4*>(qkv + static_cast<size_t>(base) * QKV_LD);
+    float4* dst = reinterpret_cast<float4*>(sq);
+    for (int idx = t; idx < n * (QKV_LD / 4); idx += 256) dst[idx] = src[idx];
+    for (int idx = t; idx < n * 256; idx += 256) shn[idx] = 0.f;
+  }
+  __syncthreads();
+  // pass 1: logits for both directions of every pair
+  for (int item = t; item < npairs * N_HEADS; item += 256) {
+    const int pl = item >> 4, hh = item & 15;
+    const uint32_t info = plan.pair_info[pbase + pl];
+    const int i = (info >> 6) & 63, j = info & 63;
+    float lij, lji;       // lij: source i -> target j
+    if (hh < N_SUB) {
+      const AT* er = e01 + static_cast<size_t>(pbase + pl) * E01_LD + hh * C_SUB;
+      const float* qi = sq + i * QKV_LD + hh * C_SUB;
+      const float* qj = sq + j * QKV_LD + hh * C_SUB;
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int d = 0; d < C_SUB; ++d) {
+        const float ev = to_f32(er[d]);
+        a = fmaf(qj[d] * qi[256 + d], ev, a);     // q[target j] * k[source i]
+        b = fmaf(qi[d] * qj[256 + d], ev, b);     // q[target i] * k[source j]
+      }
+      lij = a * 0.25f;
+      lji = b * 0.25f;
+      slog[(j * n + i) * N_HEADS + 2 + hh] = lij;
+      slog[(i * n + j) * N_HEADS + 2 + hh] = lji;
+    } else {
+      const int bit = hh - N_SUB;
+      const float v = ((pflags[pbase + pl] >> bit) & 1) ? 1.0f : -1e10f;
+      slog[(j * n + i) * N_HEADS + bit] = v;
+      slog[(i * n + j) * N_HEADS + bit] = v;
+    }
+  }
+  __syncthreads();
+  // softmax over sources for every (target, head)
+  for (int task = t; task < n * N_HEADS; task += 256) {
+    const int tg = task >> 4, hh = task & 15;
+    float* row = slog + static_cast<size_t>(tg) * n * N_HEADS + hh;
+    float mx = -INFINITY;
+    for (int s_ = 0; s_ < n; ++s_)
+      if (s_ != tg) mx = fmaxf(mx, row[s_ * N_HEADS]);
+    float den = 0.f;
+    for (int s_ = 0; s_ < n; ++s_)
+      if (s_ != tg) {
+        const float ex = act_exp<kFast>(row[s_ * N_HEADS] - mx);
+        row[s_ * N_HEADS] = ex;
+        den += ex;
+      }
+    const float inv = 1.0f / (den + 1e-16f);
+    for (int s_ = 0; s_ < n; ++s_)
+      if (s_ != tg) row[s_ * N_HEADS] *= inv;
+  }
+  __syncthreads();
+  // pass 2: messages; thread t owns value channel t of every atom
+  {
+    const int hh = t >> 4;
+    const AT* e1 = e01 + static_cast<size_t>(pbase) * E01_LD + 256 + t;
+#pragma unroll 4
+    for (int pl = 0; pl < npairs; ++pl) {
+      const uint32_t info = plan.pair_info[pbase + pl];
+      const int i = (info >> 6) & 63, j = info & 63;
+      const float ev = to_f32(e1[static_cast<size_t>(pl) * E01_LD]);
+      const float aij = slog[(j * n + i) * N_HEADS + hh], aji = slog[(i * n + j) * N_HEADS + hh];
+      shn[j * 256 + t] = fmaf(aij * sq[i * QKV_LD + 512 + t], ev, shn[j * 256 + t]);
+      shn[i * 256 + t] = fmaf(aji * sq[j * QKV_LD + 512 + t], ev, shn[i * 256 + t]);
+    }
+  }
+  for (int a = 0; a < n; ++a) {
+    const float v = shn[a * 256 + t];
+    hn[static_cast<size_t>(base + a) * 256 + t] = v;
+    hnb[static_cast<size_t>(base + a) * 256 + t] = from_f32<AT>(v);
+  }
+}
+
 // h1 = modulate(LN(h_in + ng1 * hn), nsh2, nsc2)   (dmt.py:159-161)
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_node_update1(Plan plan, const float* __restrict__ h, const float* __restrict__ hn,
@@ -455,33 +565,57 @@ __global__ void __launch_bounds__(256) k_edge_update2(Plan plan, const float* __
   store2<AT>(X + static_cast<size_t>(p) * 128 + 64 + 2 * lane, v0, v1);
 }
 
-// Z[d] = modulate(LN(input_lin([h_r | h_c | e | dist])), csh, csc) for the directed edge d = 2p + dir:
-// dir 0 -> (r=i, c=j), dir 1 -> (r=j, c=i)    (dmt.py:39-44)
+// Directed edges are stored source-major: d = 2*poff[mol] + r*(n-1) + (c - (c > r)).
+// Z[d] = modulate(LN(input_lin([h_r | h_c | e | dist])), csh, csc)   (dmt.py:39-44); one warp per SOURCE atom r:
+// the h_r part of input_lin stays in registers, the h_c rows of the molecule come from L1.
+// Also emits the adjacency bits per directed edge for the coordinate head.
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const float* __restrict__ ab, const AT* __restrict__ gp,
-                                                  const float* __restrict__ ada, int l, AT* __restrict__ Z) {
-  const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (d >= 2 * plan.Mp) return;
-  const int p = d >> 1;
-  int mol, i, j;
-  unpack_pair(plan.pair_info[p], mol, i, j);
-  const int base = plan.noff[mol];
-  const int r = (d & 1) ? j : i, c = (d & 1) ? i : j;
+                                                  const float* __restrict__ ada, int l, const uint8_t* __restrict__ pflags,
+                                                  AT* __restrict__ Z, uint8_t* __restrict__ dflags) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= plan.Mn) return;
+  const uint32_t info = plan.node_info[m];
+  const int mol = info >> 6, r = info & 63;
+  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
   const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_COORD;
-  float v[8], a[8], g[8];
-  load8(ab + static_cast<size_t>(base + r) * 512, lane, v);
-  load8(ab + static_cast<size_t>(base + c) * 512 + 256, lane, a);
-  load8<AT>(gp + static_cast<size_t>(p) * 256, lane, g);
+  float a[8], sh[8], sc[8];
+  load8(ab + static_cast<size_t>(m) * 512, lane, a);
+  load8(ar + 0, lane, sh);
+  load8(ar + 256, lane, sc);
+  size_t d = static_cast<size_t>(2 * pbase) + static_cast<size_t>(r) * (n - 1);
+  for (int c = 0; c < n; ++c) {
+    if (c == r) continue;
+    const int p = pbase + (r < c ? pair_index(n, r, c) : pair_index(n, c, r));
+    float v[8], g[8];
+    load8(ab + static_cast<size_t>(base + c) * 512 + 256, lane, v);
+    load8<AT>(gp + static_cast<size_t>(p) * 256, lane, g);
+    float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = (v[k] + a[k]) + g[k];
-  ln256_mod<kFast>(v, ar + 0, ar + 256, lane);
-  store8<AT>(Z + static_cast<size_t>(d) * 256, lane, v);
+    for (int k = 0; k < 8; ++k) {
+      v[k] = (a[k] + v[k]) + g[k];
+      s += v[k];
+    }
+    const float mean = warp_sum(s) * (1.0f / 256.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] -= mean;
+      q += v[k] * v[k];
+    }
+    const float is = inv_std<kFast>(warp_sum(q) * (1.0f / 256.0f));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (v[k] * is) * (1.0f + sc[k]) + sh[k];
+    store8<AT>(Z + d * 256, lane, v);
+    if (lane == 0) dflags[d] = pflags[p];
+    ++d;
+  }
 }
 
 // w[d] = mean(tanh(coord_mlp.2(u1[d])) * [1, adj2d, adjsp])   (dmt.py:46-51)
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_coord_out(Plan plan, const AT* __restrict__ u1, const float* __restrict__ wc2,
-                                                   const uint8_t* __restrict__ pflags, float* __restrict__ wdir) {
+                                                   const uint8_t* __restrict__ dflags, float* __restrict__ wdir) {
   const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (d >= 2 * plan.Mp) return;
   float v[8];
@@ -497,7 +631,7 @@ __global__ void __launch_bounds__(256) k_coord_out(Plan plan, const AT* __restri
     s[o] = act_tanh<kFast>(warp_sum(acc));
   }
   if (lane == 0) {
-    const uint8_t f = pflags[d >> 1];
+    const uint8_t f = dflags[d];
     const float a2 = (f & 1) ? 1.f : 0.f, asp = (f & 2) ? 1.f : 0.f;
     wdir[d] = (s[0] + s[1] * a2 + s[2] * asp) / 3.0f;
   }
@@ -526,8 +660,7 @@ __global__ void __launch_bounds__(64) k_pos_update(Plan plan, const float* __res
       if (c == r) continue;
       const float dx = px - sp[c][0], dy = py - sp[c][1], dz = pz - sp[c][2];
       const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
-      const int d = (r < c) ? 2 * (pbase + pair_index(n, r, c)) : 2 * (pbase + pair_index(n, c, r)) + 1;
-      const float w = wdir[d];
+      const float w = wdir[static_cast<size_t>(2 * pbase) + r * (n - 1) + (c - (c > r ? 1 : 0))];
       ax += (dx / nrm * scale) * w;
       ay += (dy / nrm * scale) * w;
       az += (dz / nrm * scale) * w;
@@ -647,54 +780,107 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
   if (Mp > 0) {
     k_root_pair_flags<<<cdiv(Mp, 256), 256, 0, s>>>(plan, cond_x, cond_e, w.pflags, w.flags);
     LAUNCH_CHECK(ctx);
-    k_root_pairs<AT, kFast><<<cdiv(Mp, 4), 256, 0, s>>>(plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means,
+    k_root_pairs<AT, kFast><<<cdiv(Mp, 32), 256, 0, s>>>(plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means,
                                                         pw.root_stds, pw.edge_emb_w, pw.edge_emb_b, w.e, X,
                                                         reinterpret_cast<AT*>(w.ehid));
     LAUNCH_CHECK(ctx);
   }
 
+  const int max_n = plan.N;
+  const bool att_mol = max_n <= ATT_MOL_MAXN;
+  const size_t att_smem = att_mol_smem_bytes(max_n);
+  if (att_mol) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DS_CUDA_CHECK(cudaFuncSetAttribute(k_attention_mol<AT, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(att_mol_smem_bytes(ATT_MOL_MAXN))));
+      attr_set = true;
+    }
+  }
+  uint8_t* dflags = w.pflags + (Mp > 0 ? Mp : 1);      // adjacency bits per directed edge (source-major order)
+
   for (int l = 0; l < N_LAYERS; ++l) {
     const BlockWeights& bw = pw.blk[l];
+    const float* ada_l = w.ada + l * ADA_BLK;
     if (Mp > 0) {
-      k_rbf<AT, kFast><<<cdiv(Mp, 4), 256, 0, s>>>(plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
+      k_rbf<AT, kFast><<<cdiv(Mp, 32), 256, 0, s>>>(plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
       LAUNCH_CHECK(ctx);
-      DS_TRY(linear(ctx, X, 128, bw.edge_emb_w, 128, bw.edge_emb_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
-      k_pair_ln1<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.y1, w.ada, l, reinterpret_cast<AT*>(w.ea));
-      LAUNCH_CHECK(ctx);
+      if (kFast && (ctx->fuse_mask & 1)) {
+        // edge_emb -> LayerNorm -> modulate fused in the GEMM epilogue
+        GemmDesc g;
+        g.A = X; g.lda = 128; g.W = bw.edge_emb_w; g.ldw = 128; g.bias = bw.edge_emb_b; g.out = w.ea; g.ldo = 64;
+        g.M = Mp; g.N = 64; g.K = 128; g.a_dtype = DT_BF16; g.out_dtype = DT_BF16; g.mode = GEMM_LNMOD;
+        g.row_info = plan.pair_info; g.info_shift = 12; g.ada = ada_l; g.off_a = ADA_EDGE; g.off_b = ADA_EDGE + 64;
+        DS_TRY(gemm_tc_launch(ctx, g, s));
+      } else {
+        DS_TRY(linear(ctx, X, 128, bw.edge_emb_w, 128, bw.edge_emb_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
+        k_pair_ln1<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.y1, w.ada, l, reinterpret_cast<AT*>(w.ea));
+        LAUNCH_CHECK(ctx);
+      }
       DS_TRY(linear(ctx, w.ea, 64, bw.w01, 64, nullptr, nullptr, 0, w.e01, E01_LD, AD, Mp, E01_LD, 64, ACT_TANH, s));
     }
     k_node_ln1<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h, w.ada, l, reinterpret_cast<AT*>(w.hh));
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hh, 256, bw.wqkv, 256, bw.bqkv, nullptr, 0, w.qkv, QKV_LD, DT_F32, Mn, QKV_LD, 256, ACT_NONE, s));
-    k_attention<AT, kFast><<<Mn, 256, 0, s>>>(plan, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags, w.hn,
-                                              reinterpret_cast<AT*>(w.hnb));
+    if (att_mol) {
+      k_attention_mol<AT, kFast><<<B, 256, att_smem, s>>>(plan, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags, w.hn,
+                                                          reinterpret_cast<AT*>(w.hnb));
+    } else {
+      k_attention<AT, kFast><<<Mn, 256, 0, s>>>(plan, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags, w.hn,
+                                                reinterpret_cast<AT*>(w.hnb));
+    }
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hnb, 256, bw.n2e_w, 256, nullptr, nullptr, 0, w.pn, 64, DT_F32, Mn, 64, 256, ACT_NONE, s));
     // node stream
     k_node_update1<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h, w.hn, w.ada, l, w.h1, reinterpret_cast<AT*>(w.h1b));
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.h1b, 256, bw.ff1_w, 256, bw.ff1_b, nullptr, 0, w.f1, 512, AD, Mn, 512, 256, ACT_SILU, s));
-    DS_TRY(linear(ctx, w.f1, 512, bw.ff2_w, 512, bw.ff2_b, nullptr, 0, w.f2, 256, DT_F32, Mn, 256, 512, ACT_NONE, s));
-    k_node_update2<AT><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h1, w.f2, w.ada, l, w.h, reinterpret_cast<AT*>(w.hb));
-    LAUNCH_CHECK(ctx);
+    if (kFast && (ctx->fuse_mask & 2)) {
+      GemmDesc g;     // h = h1 + gate * FFN(h1), fp32 stream + bf16 copy from one epilogue
+      g.A = w.f1; g.lda = 512; g.W = bw.ff2_w; g.ldw = 512; g.bias = bw.ff2_b; g.out = w.h; g.ldo = 256;
+      g.M = Mn; g.N = 256; g.K = 512; g.a_dtype = DT_BF16; g.out_dtype = DT_F32; g.mode = GEMM_RESGATE;
+      g.row_info = plan.node_info; g.info_shift = 6; g.ada = ada_l; g.off_a = ADA_NODE + 1280;
+      g.resid = w.h1; g.ldres = 256; g.out2 = w.hb; g.ldo2 = 256;
+      DS_TRY(gemm_tc_launch(ctx, g, s));
+    } else {
+      DS_TRY(linear(ctx, w.f1, 512, bw.ff2_w, 512, bw.ff2_b, nullptr, 0, w.f2, 256, DT_F32, Mn, 256, 512, ACT_NONE, s));
+      k_node_update2<AT><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h1, w.f2, w.ada, l, w.h, reinterpret_cast<AT*>(w.hb));
+      LAUNCH_CHECK(ctx);
+    }
     if (Mp > 0) {
       // edge stream
       k_edge_update1<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
                                                             reinterpret_cast<AT*>(w.e1b));
       LAUNCH_CHECK(ctx);
       DS_TRY(linear(ctx, w.e1b, 64, bw.ff3_w, 64, bw.ff3_b, nullptr, 0, w.f3, 128, AD, Mp, 128, 64, ACT_SILU, s));
-      DS_TRY(linear(ctx, w.f3, 128, bw.ff4_w, 128, bw.ff4_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
-      k_edge_update2<AT><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.e1f, w.y1, w.ada, l, w.e, X);
-      LAUNCH_CHECK(ctx);
+      if (kFast && (ctx->fuse_mask & 4)) {
+        GemmDesc g;   // e = e1 + gate * FFN(e1) -> fp32 stream and the [dist | e] operand
+        g.A = w.f3; g.lda = 128; g.W = bw.ff4_w; g.ldw = 128; g.bias = bw.ff4_b; g.out = w.e; g.ldo = 64;
+        g.M = Mp; g.N = 64; g.K = 128; g.a_dtype = DT_BF16; g.out_dtype = DT_F32; g.mode = GEMM_RESGATE;
+        g.row_info = plan.pair_info; g.info_shift = 12; g.ada = ada_l; g.off_a = ADA_EDGE + 320;
+        g.resid = w.e1f; g.ldres = 64; g.out2 = X + 64; g.ldo2 = 128;
+        DS_TRY(gemm_tc_launch(ctx, g, s));
+      } else {
+        DS_TRY(linear(ctx, w.f3, 128, bw.ff4_w, 128, bw.ff4_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
+        k_edge_update2<AT><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.e1f, w.y1, w.ada, l, w.e, X);
+        LAUNCH_CHECK(ctx);
+      }
       // equivariant coordinate update
       DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, s));
       DS_TRY(linear(ctx, w.hb, 256, bw.wab, 256, bw.bab, nullptr, 0, w.ab, 512, DT_F32, Mn, 512, 256, ACT_NONE, s));
-      k_coord_ln<AT, kFast><<<cdiv(Md, 8), 256, 0, s>>>(plan, w.ab, reinterpret_cast<const AT*>(w.gp), w.ada, l,
-                                                        reinterpret_cast<AT*>(w.Z));
+      k_coord_ln<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.ab, reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
+                                                        reinterpret_cast<AT*>(w.Z), dflags);
       LAUNCH_CHECK(ctx);
-      DS_TRY(linear(ctx, w.Z, 256, bw.wc1, 256, bw.bc1, nullptr, 0, w.u1, 256, AD, Md, 256, 256, ACT_SILU, s));
-      k_coord_out<AT, kFast><<<cdiv(Md, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.u1), bw.wc2, w.pflags, w.wdir);
-      LAUNCH_CHECK(ctx);
+      if (kFast && (ctx->fuse_mask & 8)) {
+        GemmDesc g;   // coord_mlp.0 -> SiLU -> coord_mlp.2 -> tanh -> adjacency-weighted mean, all in the epilogue
+        g.A = w.Z; g.lda = 256; g.W = bw.wc1; g.ldw = 256; g.bias = bw.bc1; g.M = Md; g.N = 256; g.K = 256;
+        g.a_dtype = DT_BF16; g.mode = GEMM_COORD; g.wc2 = bw.wc2; g.pflags = dflags; g.wdir = w.wdir;
+        DS_TRY(gemm_tc_launch(ctx, g, s));
+      } else {
+        DS_TRY(linear(ctx, w.Z, 256, bw.wc1, 256, bw.bc1, nullptr, 0, w.u1, 256, AD, Md, 256, 256, ACT_SILU, s));
+        k_coord_out<AT, kFast><<<cdiv(Md, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.u1), bw.wc2, dflags, w.wdir);
+        LAUNCH_CHECK(ctx);
+      }
     }
     k_pos_update<<<B, 64, 0, s>>>(plan, w.wdir, bw.coord_scale, w.pos);
     LAUNCH_CHECK(ctx);
@@ -775,7 +961,7 @@ size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf) 
   w.gp = a.take(mp * 256 * es);
   w.ehid = a.take(mp * 192 * es);
   w.eh1 = a.take(mp * 128 * es);
-  w.pflags = static_cast<uint8_t*>(a.take(mp));
+  w.pflags = static_cast<uint8_t*>(a.take(mp + md));   // [Mp] per pair + [2Mp] per directed edge
   w.Z = a.take(md * 256 * es);
   w.u1 = a.take(md * 256 * es);
   w.wdir = static_cast<float*>(a.take(md * 4));

@@ -1,12 +1,20 @@
-// Hand-written sm_100a GEMM:  out[M,N] = act(A[M,K] * W[N,K]^T + bias + addmat),  bf16 in, fp32 accumulate.
+// Hand-written sm_100a GEMM:  out[M,N] = epilogue(A[M,K] * W[N,K]^T),  bf16 in, fp32 accumulate in TMEM.
 //
-// Persistent, warp-specialised:  warp 4 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B tiles, mbarrier
-// pipeline),  warp 5 = tcgen05.mma issuer + TMEM owner (one elected thread, accumulators double-buffered in
-// TMEM so the epilogue of tile i overlaps the MMAs of tile i+1),  warps 0-3 = epilogue (tcgen05.ld -> bias /
-// activation -> bf16|fp32 global stores, one output row per thread).
+// Persistent, warp-specialised, 320 threads:
+//   warp 8      TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B tiles, mbarrier ring of kStages slots)
+//   warp 9      tcgen05.mma issuer + TMEM owner (one elected thread; TWO accumulator stages in TMEM)
+//   warps 0-3   epilogue group 0  (accumulator stage 0, even tiles)
+//   warps 4-7   epilogue group 1  (accumulator stage 1, odd tiles)
+// Each epilogue thread owns one full output row of its tile (tcgen05.ld 32x32b), so row-wise epilogues
+// (LayerNorm, dot products) need no cross-thread traffic.  bf16 outputs are staged in swizzled shared memory
+// and written with TMA stores (coalesced, bounds-clipped); the two groups let the epilogue of tile i overlap
+// the MMAs of tiles i+1, i+2.
 //
-// This one kernel serves every dense contraction of DMT / SpecFormer in bf16 mode (reference: all nn.Linear
-// calls of models/dmt.py, models/layers.py, models/specformer.py — SURVEY.md §2.1 'addmm' row).
+// Epilogue modes (fusions of the reference's elementwise ops into the producing contraction):
+//   STORE    act(acc + bias + addmat)                                  every nn.Linear (+SiLU/tanh/GELU)
+//   LNMOD    modulate(LayerNorm(acc + bias), shift[mol], scale[mol])    dmt.py:139,149 (edge_emb -> norm1_edge)
+//   RESGATE  resid + gate[mol] * (acc + bias) -> fp32 stream + bf16 copy  dmt.py:162-163,168-169 (FFN residuals)
+//   COORD    mean(tanh(W2 . SiLU(acc + bias)) * [1, adj2d, adjsp])       dmt.py:32-35,45-51 (coord_mlp + heads)
 #include "context.cuh"
 #include "ptx_sm100.cuh"
 
@@ -15,64 +23,85 @@ namespace {
 constexpr int BM = 128;   // UMMA M (cta_group::1)
 constexpr int BK = 64;    // one 128-byte swizzle atom of bf16
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kStageBox = 32 * 128;   // one staging box: 32 rows x 128 bytes
 
-template <int BN>
+template <int BN, int MODE, bool TMA_OUT>
 struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kWBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStagingBytes = TMA_OUT ? kEpiWarps * 2 * kStageBox : 0;
+  static constexpr int kAuxBytes = 2 * 256 * 4 /*bias, per group*/ + (MODE == GEMM_COORD ? 256 * 16 : 0) + 256 /*barriers*/;
+  static constexpr int kBudget = 220 * 1024 - kStagingBytes - kAuxBytes;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kAuxBytes + 1024 /*align slack*/;
 };
 
 struct Epi {
   const float* bias;
   const float* addmat;
-  void* out;
+  void* out;            // direct-store output (fp32, or bf16 when not TMA_OUT)
   int ldo, ldadd;
   int out_dtype;
   int act;
+  // row -> molecule -> adaLN row
+  const uint32_t* row_info;
+  int info_shift;
+  const float* ada;     // pre-offset to the block's base; row stride ADA_LD
+  int off_a, off_b;     // LNMOD: shift, scale offsets; RESGATE: off_a = gate offset
+  const float* resid;
+  int ldres;
+  const float* wc2;     // COORD: [3,256]
+  const uint8_t* pflags;
+  float* wdir;
 };
 
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// write 64 bf16 (one 128-byte row) of staging row `r` (0..31) with the SWIZZLE_128B pattern
+__device__ __forceinline__ void stage_row_bf16(uint8_t* box, int r, const float (&f)[64]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 u;
+    u.x = pack_bf16(f[c * 8 + 0], f[c * 8 + 1]);
+    u.y = pack_bf16(f[c * 8 + 2], f[c * 8 + 3]);
+    u.z = pack_bf16(f[c * 8 + 4], f[c * 8 + 5]);
+    u.w = pack_bf16(f[c * 8 + 6], f[c * 8 + 7]);
+    *reinterpret_cast<uint4*>(box + r * 128 + ((c ^ (r & 7)) << 4)) = u;
+  }
+}
+
+// direct (register -> global) store of CH consecutive columns of one row
 template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[CH], const Epi& ep, int row, int col0, int N) {
-  float f[CH];
-#pragma unroll
-  for (int i = 0; i < CH; ++i) f[i] = __uint_as_float(v[i]);
-  if (ep.bias) {
-#pragma unroll
-    for (int i = 0; i < CH; ++i)
-      if (col0 + i < N) f[i] += __ldg(ep.bias + col0 + i);
-  }
-  if (ep.addmat) {
-    const float* ar = ep.addmat + static_cast<size_t>(row) * ep.ldadd + col0;
-#pragma unroll
-    for (int i = 0; i < CH; ++i)
-      if (col0 + i < N) f[i] += __ldg(ar + i);
-  }
-  if (ep.act != ACT_NONE) {
-#pragma unroll
-    for (int i = 0; i < CH; ++i) f[i] = apply_act<true>(f[i], ep.act);
-  }
+__device__ __forceinline__ void direct_store(const float (&f)[CH], void* out, int out_dtype, int ldo, int row, int col0, int N) {
   const bool full = (col0 + CH <= N);
-  if (ep.out_dtype == DT_BF16) {
-    bf16* o = reinterpret_cast<bf16*>(ep.out) + static_cast<size_t>(row) * ep.ldo + col0;
+  if (out_dtype == DT_BF16) {
+    bf16* o = reinterpret_cast<bf16*>(out) + static_cast<size_t>(row) * ldo + col0;
     if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
       for (int i = 0; i < CH; i += 8) {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(f[i], f[i + 1]);
-        __nv_bfloat162 p1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
-        __nv_bfloat162 p3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
         uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&p0);
-        u.y = *reinterpret_cast<uint32_t*>(&p1);
-        u.z = *reinterpret_cast<uint32_t*>(&p2);
-        u.w = *reinterpret_cast<uint32_t*>(&p3);
+        u.x = pack_bf16(f[i], f[i + 1]); u.y = pack_bf16(f[i + 2], f[i + 3]);
+        u.z = pack_bf16(f[i + 4], f[i + 5]); u.w = pack_bf16(f[i + 6], f[i + 7]);
         *reinterpret_cast<uint4*>(o + i) = u;
       }
     } else {
@@ -81,7 +110,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[CH], const Ep
         if (col0 + i < N) o[i] = __float2bfloat16_rn(f[i]);
     }
   } else {
-    float* o = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldo + col0;
+    float* o = reinterpret_cast<float*>(out) + static_cast<size_t>(row) * ldo + col0;
     if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
       for (int i = 0; i < CH; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
@@ -93,20 +122,33 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[CH], const Ep
   }
 }
 
-template <int BN>
+template <int CH>
+__device__ __forceinline__ void load_acc(uint32_t taddr, float (&f)[CH]) {
+  uint32_t v[CH];
+  if constexpr (CH == 64) ptx::tmem_ld64_sync(taddr, v);
+  else if constexpr (CH == 32) ptx::tmem_ld32_sync(taddr, v);
+  else ptx::tmem_ld16_sync(taddr, v);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) f[i] = __uint_as_float(v[i]);
+}
+
+template <int BN, int MODE, bool TMA_OUT>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, Epi ep, int M, int N,
-               int K) {
-  using C = Cfg<BN>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO, Epi ep, int M, int N, int K) {
+  using C = Cfg<BN, MODE, TMA_OUT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smW = smem + C::kStages * C::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
-  uint64_t* empty_bar = bars + C::kStages;         // [kStages]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * C::kStages;     // [2]        MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * C::kStages + 2;   // [2]     epilogue -> MMA
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;                 // 1024-aligned (stage sizes are multiples of 1 KB)
+  float* sbias = reinterpret_cast<float*>(staging + C::kStagingBytes);   // [2][256]
+  float4* swc2 = reinterpret_cast<float4*>(sbias + 512);                 // COORD: [256] (w0, w1, w2, bias)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + 2048 + (MODE == GEMM_COORD ? 4096 : 0));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tfull_bar = bars + 2 * C::kStages;
+  uint64_t* tempty_bar = bars + 2 * C::kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -116,26 +158,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int k_blocks = (K + BK - 1) / BK;
   const int num_tiles = m_tiles * n_tiles;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
+    if (TMA_OUT) ptx::prefetch_tmap(&tmO);
     for (int i = 0; i < C::kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], kEpiWarps * 32);
+      ptx::mbar_init(&tempty_bar[i], 128);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 5) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 9) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+  if constexpr (MODE == GEMM_COORD) {
+    if (threadIdx.x < 256)
+      swc2[threadIdx.x] = make_float4(ep.wc2[threadIdx.x], ep.wc2[256 + threadIdx.x], ep.wc2[512 + threadIdx.x],
+                                      ep.bias[threadIdx.x]);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -152,15 +200,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -175,47 +224,167 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t wd = ptx::umma_smem_desc_sw128(w_addr + k * UMMA_K * 2);
             ptx::umma_bf16(d_tmem, ad, wd, idesc, (kb | k) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);                  // smem slot free once these MMAs retire
-          if (kb == k_blocks - 1) ptx::umma_commit(&tfull_bar[as]);   // accumulator ready
+          ptx::umma_commit(&empty_bar[stage]);
+          if (kb == k_blocks - 1) ptx::umma_commit(&tfull_bar[as]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 0..3 <-> TMEM lane quadrants 0..3) =====================
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    // ===================== epilogue: group g owns accumulator stage g and every second tile =====================
+    const int g = warp >> 2, wq = warp & 3;
+    const int gtid = threadIdx.x & 127;
+    float* gb = sbias + g * 256;
+    uint8_t* my_stage = staging + (TMA_OUT ? warp * 2 * kStageBox : 0);
+    int sb = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      if ((it & 1) != g) continue;
+      const uint32_t gphase = (it >> 1) & 1;
       const int m0 = (t / n_tiles) * BM;
       const int n0 = (t % n_tiles) * BN;
-      ptx::mbar_wait(&tfull_bar[as], aphase);
+      if constexpr (MODE != GEMM_COORD) {
+        named_bar_sync(1 + g, 128);                  // everyone is done with the previous tile's bias
+        for (int i = gtid; i < BN; i += 128) gb[i] = (ep.bias && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
+        named_bar_sync(1 + g, 128);
+      }
+      ptx::mbar_wait(&tfull_bar[g], gphase);
       ptx::tc_fence_after();
-      const int row = m0 + warp * 32 + lane;
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(as * BN);
-      if constexpr (BN >= 32) {
+      const int row = m0 + wq * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(g * BN);
+
+      if constexpr (MODE == GEMM_STORE) {
+        constexpr int CH = BN >= 64 ? (TMA_OUT ? 64 : 32) : BN;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld32(t_addr + c, v);
-          ptx::tmem_ld_wait();
-          if (row < M && n0 + c < N) epilogue_chunk<32>(v, ep, row, n0 + c, N);
+        for (int c = 0; c < BN; c += CH) {
+          float f[CH];
+          load_acc<CH>(t_addr + c, f);
+#pragma unroll
+          for (int i = 0; i < CH; ++i) f[i] += gb[c + i];
+          if (ep.addmat && row_ok) {
+            const float* ar = ep.addmat + static_cast<size_t>(row) * ep.ldadd + n0 + c;
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+              if (n0 + c + i < N) f[i] += __ldg(ar + i);
+          }
+          if (ep.act != ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) f[i] = apply_act<true>(f[i], ep.act);
+          }
+          if constexpr (TMA_OUT) {
+            if (lane == 0) tma_store_wait_read<1>();       // the box we are about to overwrite has been read
+            __syncwarp();
+            uint8_t* box = my_stage + sb * kStageBox;
+            stage_row_bf16(box, lane, f);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (n0 + c < N && m0 + wq * 32 < M) tma_store_2d(&tmO, box, n0 + c, m0 + wq * 32);
+              tma_store_commit();
+            }
+            sb ^= 1;
+          } else {
+            if (row_ok && n0 + c < N) direct_store<CH>(f, ep.out, ep.out_dtype, ep.ldo, row, n0 + c, N);
+          }
         }
-      } else {
-        uint32_t v[16];
-        ptx::tmem_ld16(t_addr, v);
-        ptx::tmem_ld_wait();
-        if (row < M) epilogue_chunk<16>(v, ep, row, n0, N);
+      } else if constexpr (MODE == GEMM_LNMOD) {
+        // BN == N == 64: the thread holds the whole row
+        float f[64];
+        load_acc<64>(t_addr, f);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) { f[i] += gb[i]; s += f[i]; }
+        const float mean = s * (1.0f / 64.0f);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) { f[i] -= mean; q += f[i] * f[i]; }
+        const float is = rsqrtf(q * (1.0f / 64.0f) + 1e-6f);
+        const uint32_t mol = row_ok ? (ep.row_info[row] >> ep.info_shift) : 0u;
+        const float* ar = ep.ada + static_cast<size_t>(mol) * ADA_LD;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(ar + ep.off_a + i));
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(ar + ep.off_b + i));
+          f[i + 0] = (f[i + 0] * is) * (1.0f + sc.x) + sh.x;
+          f[i + 1] = (f[i + 1] * is) * (1.0f + sc.y) + sh.y;
+          f[i + 2] = (f[i + 2] * is) * (1.0f + sc.z) + sh.z;
+          f[i + 3] = (f[i + 3] * is) * (1.0f + sc.w) + sh.w;
+        }
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* box = my_stage + sb * kStageBox;
+        stage_row_bf16(box, lane, f);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (m0 + wq * 32 < M) tma_store_2d(&tmO, box, 0, m0 + wq * 32);
+          tma_store_commit();
+        }
+        sb ^= 1;
+      } else if constexpr (MODE == GEMM_RESGATE) {
+        const uint32_t mol = row_ok ? (ep.row_info[row] >> ep.info_shift) : 0u;
+        const float* gr = ep.ada + static_cast<size_t>(mol) * ADA_LD + ep.off_a;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          float f[64];
+          load_acc<64>(t_addr + c, f);
+          if (row_ok) {
+            const float* rr = ep.resid + static_cast<size_t>(row) * ep.ldres + n0 + c;
+            float* orow = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldo + n0 + c;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rr + i));
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gr + n0 + c + i));
+              f[i + 0] = r4.x + g4.x * (f[i + 0] + gb[c + i + 0]);
+              f[i + 1] = r4.y + g4.y * (f[i + 1] + gb[c + i + 1]);
+              f[i + 2] = r4.z + g4.z * (f[i + 2] + gb[c + i + 2]);
+              f[i + 3] = r4.w + g4.w * (f[i + 3] + gb[c + i + 3]);
+              *reinterpret_cast<float4*>(orow + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            }
+          }
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* box = my_stage + sb * kStageBox;
+          stage_row_bf16(box, lane, f);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (m0 + wq * 32 < M) tma_store_2d(&tmO, box, n0 + c, m0 + wq * 32);
+            tma_store_commit();
+          }
+          sb ^= 1;
+        }
+      } else {   // GEMM_COORD, BN == N == 256
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 256; c += 32) {
+          float f[32];
+          load_acc<32>(t_addr + c, f);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 w = swc2[c + i];
+            const float v = act_silu<true>(f[i] + w.w);
+            s0 = fmaf(v, w.x, s0);
+            s1 = fmaf(v, w.y, s1);
+            s2 = fmaf(v, w.z, s2);
+          }
+        }
+        if (row_ok) {
+          const uint8_t fl = ep.pflags[row];            // per directed edge (k_coord_ln)
+          const float a2 = (fl & 1) ? 1.f : 0.f, asp = (fl & 2) ? 1.f : 0.f;
+          ep.wdir[row] = (act_tanh<true>(s0) + act_tanh<true>(s1) * a2 + act_tanh<true>(s2) * asp) / 3.0f;
+        }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      ptx::mbar_arrive(&tempty_bar[g]);
     }
+    if (TMA_OUT && lane == 0) tma_store_wait_all();
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
   }
@@ -225,11 +394,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap(DsContext* ctx, CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+int make_tmap(DsContext* ctx, CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -239,25 +408,35 @@ int make_tmap(DsContext* ctx, CUtensorMap* map, const void* base, int rows, int 
   return DS_OK;
 }
 
-template <int BN>
-int launch_bn(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
-  using C = Cfg<BN>;
-  CUtensorMap tmA, tmW;
-  DS_TRY(make_tmap(ctx, &tmA, g.A, g.M, g.K, g.lda, BM));
-  DS_TRY(make_tmap(ctx, &tmW, g.W, g.N, g.K, g.ldw, BN));
-  Epi ep{g.bias, g.addmat, g.out, g.ldo, g.ldadd, g.out_dtype, g.act};
+template <int BN, int MODE, bool TMA_OUT>
+int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
+  using C = Cfg<BN, MODE, TMA_OUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmW, tmO;
+  DS_TRY(make_tmap(ctx, &tmA, g.A, g.M, g.K, g.lda, BK, BM));
+  DS_TRY(make_tmap(ctx, &tmW, g.W, g.N, g.K, g.ldw, BK, BN));
+  if (TMA_OUT) {
+    const void* ob = (MODE == GEMM_RESGATE) ? g.out2 : g.out;
+    const int ld = (MODE == GEMM_RESGATE) ? g.ldo2 : g.ldo;
+    DS_TRY(make_tmap(ctx, &tmO, ob, g.M, g.N, ld, 64, 32));
+  } else {
+    tmO = tmA;
+  }
+  Epi ep;
+  ep.bias = g.bias; ep.addmat = g.addmat; ep.out = g.out; ep.ldo = g.ldo; ep.ldadd = g.ldadd;
+  ep.out_dtype = g.out_dtype; ep.act = g.act;
+  ep.row_info = g.row_info; ep.info_shift = g.info_shift; ep.ada = g.ada; ep.off_a = g.off_a; ep.off_b = g.off_b;
+  ep.resid = g.resid; ep.ldres = g.ldres; ep.wc2 = g.wc2; ep.pflags = g.pflags; ep.wdir = g.wdir;
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(tmA, tmW, ep, g.M, g.N, g.K);
+  gemm_tc_kernel<BN, MODE, TMA_OUT><<<grid, kThreads, C::kSmemBytes, s>>>(tmA, tmW, tmO, ep, g.M, g.N, g.K);
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;
-  return DS_OK;
-}
-
-template <int BN>
-int set_attr() {
-  DS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
   return DS_OK;
 }
 
@@ -269,11 +448,6 @@ int gemm_tc_init(DsContext* ctx) {
   DS_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   DS_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, DS_ERR_CUDA, "cuTensorMapEncodeTiled not available");
   ctx->encode_tiled = fn;
-  DS_TRY(set_attr<16>());
-  DS_TRY(set_attr<32>());
-  DS_TRY(set_attr<64>());
-  DS_TRY(set_attr<128>());
-  DS_TRY(set_attr<256>());
   return DS_OK;
 }
 
@@ -283,9 +457,26 @@ int gemm_tc_launch(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
   DS_CHECK((g.lda % 8) == 0 && (g.ldw % 8) == 0, DS_ERR_INVALID, "gemm_tc: lda/ldw must be multiples of 8 (16 B rows)");
   DS_CHECK((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.W) & 15) == 0, DS_ERR_INVALID,
            "gemm_tc: A/W must be 16-byte aligned");
-  if (g.N <= 16) return launch_bn<16>(ctx, g, s);
-  if (g.N <= 32) return launch_bn<32>(ctx, g, s);
-  if (g.N <= 64) return launch_bn<64>(ctx, g, s);
-  if (g.N <= 128) return launch_bn<128>(ctx, g, s);
-  return launch_bn<256>(ctx, g, s);
+  switch (g.mode) {
+    case GEMM_LNMOD:
+      DS_CHECK(g.N == 64 && g.out_dtype == DT_BF16, DS_ERR_INVALID, "gemm_tc LNMOD: N must be 64, bf16 out");
+      return launch_cfg<64, GEMM_LNMOD, true>(ctx, g, s);
+    case GEMM_RESGATE:
+      DS_CHECK((g.N == 64 || g.N == 256) && g.out_dtype == DT_F32 && g.out2 != nullptr, DS_ERR_INVALID, "gemm_tc RESGATE: N in {64,256}");
+      if (g.N == 64) return launch_cfg<64, GEMM_RESGATE, true>(ctx, g, s);
+      return launch_cfg<256, GEMM_RESGATE, true>(ctx, g, s);
+    case GEMM_COORD:
+      DS_CHECK(g.N == 256, DS_ERR_INVALID, "gemm_tc COORD: N must be 256");
+      return launch_cfg<256, GEMM_COORD, false>(ctx, g, s);
+    default:
+      break;
+  }
+  // TMA stores clip the inner dimension at 16-byte granularity (measured): N must be a multiple of 8 bf16
+  const bool tma_out = g.out_dtype == DT_BF16 && g.N >= 64 && (g.N % 8) == 0 && (g.ldo % 8) == 0 &&
+                       (reinterpret_cast<uintptr_t>(g.out) & 15) == 0;
+  if (g.N <= 16) return launch_cfg<16, GEMM_STORE, false>(ctx, g, s);
+  if (g.N <= 32) return launch_cfg<32, GEMM_STORE, false>(ctx, g, s);
+  if (g.N <= 64) return tma_out ? launch_cfg<64, GEMM_STORE, true>(ctx, g, s) : launch_cfg<64, GEMM_STORE, false>(ctx, g, s);
+  if (g.N <= 128) return tma_out ? launch_cfg<128, GEMM_STORE, true>(ctx, g, s) : launch_cfg<128, GEMM_STORE, false>(ctx, g, s);
+  return tma_out ? launch_cfg<256, GEMM_STORE, true>(ctx, g, s) : launch_cfg<256, GEMM_STORE, false>(ctx, g, s);
 }

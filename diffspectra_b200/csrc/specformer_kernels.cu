@@ -35,64 +35,74 @@ __global__ void __launch_bounds__(128) k_patch_embed(const float* __restrict__ s
   zb[o] = from_f32<AT>(acc);
 }
 
-// one warp per (b, head, query i): s_j = scale * q_i . k_j + prev[b,h,i,j]; scores <- s; a = softmax_j(s);
-// out[b, i, h*8:(h+1)*8] = sum_j a_j v_j                    (specformer.py:395-419)
+// One CTA per (molecule, head): K and V of the head live in shared memory (rows padded to 12 floats so that the
+// 128-bit reads of consecutive keys are bank-conflict free); each warp takes queries i = w, w+8, ...:
+// s_j = scale * q_i . k_j + prev[b,h,i,j]; scores <- s; a = softmax_j(s); out[b, i, h*8:(h+1)*8] = sum_j a_j v_j
+// (specformer.py:395-419).  HBM traffic = the residual score tensor (read + write), everything else stays on chip.
+constexpr int SPEC_MAXQ = 352;
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_spec_attn(const float* __restrict__ qkv, float* __restrict__ scores, int first,
-                                                   const float* __restrict__ scale_p, int Q, int total_rows,
-                                                   AT* __restrict__ out) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= total_rows) return;
-  const int i = row % Q, h = (row / Q) % SH, bi = row / (Q * SH);
+                                                   const float* __restrict__ scale_p, int Q, AT* __restrict__ out) {
+  __shared__ __align__(16) float sk[SPEC_MAXQ * 12];
+  __shared__ __align__(16) float sv[SPEC_MAXQ * 12];
+  const int h = blockIdx.x % SH, bi = blockIdx.x / SH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float scale = scale_p[0];
-  const float* qr = qkv + (static_cast<size_t>(bi) * Q + i) * 384 + h * SK;
-  float qv[SK];
-#pragma unroll
-  for (int d = 0; d < SK; ++d) qv[d] = qr[d];
-  float* sr = scores + (static_cast<size_t>(bi) * SH + h) * Q * Q + static_cast<size_t>(i) * Q;
-  constexpr int MAXJ = 11;    // ceil(347 / 32)
-  float sv[MAXJ];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int it = 0; it < MAXJ; ++it) {
-    const int j = lane + 32 * it;
-    sv[it] = -INFINITY;
-    if (j < Q) {
-      const float* kr = qkv + (static_cast<size_t>(bi) * Q + j) * 384 + 128 + h * SK;
-      float dot = 0.f;
-#pragma unroll
-      for (int d = 0; d < SK; ++d) dot = fmaf(qv[d], kr[d], dot);
-      float s = dot * scale;
-      if (!first) s += sr[j];
-      sr[j] = s;
-      sv[it] = s;
-      mx = fmaxf(mx, s);
-    }
+  for (int idx = threadIdx.x; idx < Q * 2; idx += 256) {
+    const int j = idx >> 1, half = idx & 1;
+    const float* src = qkv + (static_cast<size_t>(bi) * Q + j) * 384 + h * SK + half * 4;
+    *reinterpret_cast<float4*>(sk + j * 12 + half * 4) = *reinterpret_cast<const float4*>(src + 128);
+    *reinterpret_cast<float4*>(sv + j * 12 + half * 4) = *reinterpret_cast<const float4*>(src + 256);
   }
-  mx = warp_max(mx);
-  float den = 0.f;
-  float o[SK];
+  __syncthreads();
+  constexpr int MAXJ = SPEC_MAXQ / 32;    // 11
+  for (int i = warp; i < Q; i += 8) {
+    const float* qr = qkv + (static_cast<size_t>(bi) * Q + i) * 384 + h * SK;
+    const float4 q0 = *reinterpret_cast<const float4*>(qr), q1 = *reinterpret_cast<const float4*>(qr + 4);
+    float* sr = scores + (static_cast<size_t>(bi) * SH + h) * Q * Q + static_cast<size_t>(i) * Q;
+    float svv[MAXJ];
+    float mx = -INFINITY;
 #pragma unroll
-  for (int d = 0; d < SK; ++d) o[d] = 0.f;
-#pragma unroll
-  for (int it = 0; it < MAXJ; ++it) {
-    const int j = lane + 32 * it;
-    if (j < Q) {
-      const float e = act_exp<kFast>(sv[it] - mx);
-      den += e;
-      const float* vr = qkv + (static_cast<size_t>(bi) * Q + j) * 384 + 256 + h * SK;
-#pragma unroll
-      for (int d = 0; d < SK; ++d) o[d] = fmaf(e, vr[d], o[d]);
+    for (int it = 0; it < MAXJ; ++it) {
+      const int j = lane + 32 * it;
+      svv[it] = -INFINITY;
+      if (j < Q) {
+        const float4 k0 = *reinterpret_cast<const float4*>(sk + j * 12), k1 = *reinterpret_cast<const float4*>(sk + j * 12 + 4);
+        float dot = q0.x * k0.x;
+        dot = fmaf(q0.y, k0.y, dot); dot = fmaf(q0.z, k0.z, dot); dot = fmaf(q0.w, k0.w, dot);
+        dot = fmaf(q1.x, k1.x, dot); dot = fmaf(q1.y, k1.y, dot); dot = fmaf(q1.z, k1.z, dot); dot = fmaf(q1.w, k1.w, dot);
+        float sc = dot * scale;
+        if (!first) sc += sr[j];
+        sr[j] = sc;
+        svv[it] = sc;
+        mx = fmaxf(mx, sc);
+      }
     }
-  }
-  den = warp_sum(den);
+    mx = warp_max(mx);
+    float den = 0.f;
+    float o[SK];
 #pragma unroll
-  for (int d = 0; d < SK; ++d) o[d] = warp_sum(o[d]);
-  if (lane < SK) {
-    float v = o[0];
+    for (int d = 0; d < SK; ++d) o[d] = 0.f;
 #pragma unroll
-    for (int d = 1; d < SK; ++d) v = (lane == d) ? o[d] : v;
-    out[(static_cast<size_t>(bi) * Q + i) * SD + h * SK + lane] = from_f32<AT>(v / den);
+    for (int it = 0; it < MAXJ; ++it) {
+      const int j = lane + 32 * it;
+      if (j < Q) {
+        const float e = act_exp<kFast>(svv[it] - mx);
+        den += e;
+        const float4 v0 = *reinterpret_cast<const float4*>(sv + j * 12), v1 = *reinterpret_cast<const float4*>(sv + j * 12 + 4);
+        o[0] = fmaf(e, v0.x, o[0]); o[1] = fmaf(e, v0.y, o[1]); o[2] = fmaf(e, v0.z, o[2]); o[3] = fmaf(e, v0.w, o[3]);
+        o[4] = fmaf(e, v1.x, o[4]); o[5] = fmaf(e, v1.y, o[5]); o[6] = fmaf(e, v1.z, o[6]); o[7] = fmaf(e, v1.w, o[7]);
+      }
+    }
+    den = warp_sum(den);
+#pragma unroll
+    for (int d = 0; d < SK; ++d) o[d] = warp_sum(o[d]);
+    if (lane < SK) {
+      float v = o[0];
+#pragma unroll
+      for (int d = 1; d < SK; ++d) v = (lane == d) ? o[d] : v;
+      out[(static_cast<size_t>(bi) * Q + i) * SD + h * SK + lane] = from_f32<AT>(v / den);
+    }
   }
 }
 
@@ -167,9 +177,7 @@ int spec_impl(DsContext* ctx, const PackedWeights& pw, const float* const* spect
     for (int l = 0; l < 3; ++l) {
       const SpecLayerWeights& sl = pw.sl[l];
       DS_TRY(linear(ctx, w.zb, SD, sl.wqkv, SD, sl.bqkv, nullptr, 0, w.qkv, 384, DT_F32, rows, 384, SD, ACT_NONE, s));
-      const int arows = nb * SH * Q;
-      k_spec_attn<AT, kFast><<<cdiv(arows, 8), 256, 0, s>>>(w.qkv, w.scores, l == 0, sl.scale, Q, arows,
-                                                            reinterpret_cast<AT*>(w.att));
+      k_spec_attn<AT, kFast><<<nb * SH, 256, 0, s>>>(w.qkv, w.scores, l == 0, sl.scale, Q, reinterpret_cast<AT*>(w.att));
       LAUNCH_CHECK(ctx);
       DS_TRY(linear(ctx, w.att, SD, sl.wo, SD, sl.bo, nullptr, 0, w.o, SD, DT_F32, rows, SD, SD, ACT_NONE, s));
       const size_t total = static_cast<size_t>(rows) * SD;

@@ -91,3 +91,67 @@ def test_gemm_simt_fp32(ctx, M, N, K):
     out = torch.empty(M, N, device='cuda')
     run_gemm(ctx, False, A, W, bias, None, out, L.ACT_NONE, M, N, K)
     assert (out - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+ADA_LD = 19584
+
+
+def _fused_inputs(M, N, K, n_mol, seed):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    A = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    W = (torch.randn(N, K, device='cuda', generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g) * 0.1
+    mol = torch.sort(torch.randint(0, n_mol, (M,), device='cuda', generator=g)).values
+    info = (mol << 12).to(torch.int32)
+    ada = torch.randn(n_mol, ADA_LD, device='cuda', generator=g) * 0.5
+    return A, W, bias, mol, info, ada
+
+
+@pytest.mark.parametrize('M', [300, 128, 5000])
+def test_gemm_fused_lnmod(ctx, M):
+    N, K = 64, 128
+    A, W, bias, mol, info, ada = _fused_inputs(M, N, K, 7, M)
+    off_a, off_b = 1536, 1600
+    out = torch.full((M + 8, N), -7.0, device='cuda', dtype=torch.bfloat16)
+    L.check(L.lib().ds_gemm_fused(ctx, 1, L.ptr(A), K, L.ptr(W), K, L.ptr(bias), M, N, K, L.ptr(info), 12, L.ptr(ada), off_a,
+                                  off_b, None, 0, L.ptr(out), N, None, 0, None, None, None, L.stream_ptr()), 'ds_gemm_fused')
+    torch.cuda.synchronize()
+    y = torch.nn.functional.layer_norm(A.float() @ W.float().t() + bias, (N,), eps=1e-6)
+    ref = y * (1 + ada[mol, off_b:off_b + N]) + ada[mol, off_a:off_a + N]
+    assert (out[:M].float() - ref).abs().max().item() < 5e-2
+    assert (out[M:] == -7).all()
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 64, 128), (1000, 256, 512)])
+def test_gemm_fused_resgate(ctx, M, N, K):
+    A, W, bias, mol, info, ada = _fused_inputs(M, N, K, 5, M + N)
+    off = 320
+    resid = torch.randn(M, N, device='cuda')
+    out = torch.empty(M, N, device='cuda')
+    buf2 = torch.zeros(M, 2 * N, device='cuda', dtype=torch.bfloat16)
+    out2 = buf2[:, N:]
+    L.check(L.lib().ds_gemm_fused(ctx, 2, L.ptr(A), K, L.ptr(W), K, L.ptr(bias), M, N, K, L.ptr(info), 12, L.ptr(ada), off, 0,
+                                  L.ptr(resid), N, L.ptr(out), N, L.ptr(out2), 2 * N, None, None, None, L.stream_ptr()),
+            'ds_gemm_fused')
+    torch.cuda.synchronize()
+    ref = resid + ada[mol, off:off + N] * (A.float() @ W.float().t() + bias)
+    assert (out - ref).abs().max().item() < 5e-3
+    assert (out2.float() - ref).abs().max().item() < 5e-2
+    assert (buf2[:, :N] == 0).all()
+
+
+def test_gemm_fused_coord(ctx):
+    M, N, K = 3001, 256, 256
+    A, W, bias, mol, info, ada = _fused_inputs(M, N, K, 5, 3)
+    g = torch.Generator(device='cuda').manual_seed(4)
+    wc2 = torch.randn(3, 256, device='cuda', generator=g) / 16
+    dflags = torch.randint(0, 4, (M,), device='cuda', generator=g, dtype=torch.uint8)
+    wdir = torch.full((M + 4,), -7.0, device='cuda')
+    L.check(L.lib().ds_gemm_fused(ctx, 3, L.ptr(A), K, L.ptr(W), K, L.ptr(bias), M, N, K, None, 0, None, 0, 0, None, 0, None, 0,
+                                  None, 0, L.ptr(wc2), L.ptr(dflags), L.ptr(wdir), L.stream_ptr()), 'ds_gemm_fused')
+    torch.cuda.synchronize()
+    u = torch.tanh(torch.nn.functional.silu(A.float() @ W.float().t() + bias) @ wc2.t())
+    adj = torch.stack([torch.ones(M, device='cuda'), (dflags & 1).float(), ((dflags >> 1) & 1).float()], dim=1)
+    ref = (u * adj).mean(-1)
+    assert (wdir[:M] - ref).abs().max().item() < 5e-3
+    assert (wdir[M:] == -7).all()

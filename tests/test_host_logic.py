@@ -1,0 +1,91 @@
+"""CPU-side checks: parameter manifest (names / shapes / ORDER = EMA order), C-ABI symbols, host error
+behaviour without a GPU, and the multi-process sharding logic (gloo, world_size 2)."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from tests.helpers import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('version', ['allspectra', 'ir'])
+def test_parameter_manifest_matches_reference(version):
+    from diffspectra_b200.config import get_config
+    from diffspectra_b200.model import DMT_B200
+    man = json.load(open(os.path.join(GOLDEN, 'param_manifest.json')))[version]
+    m = DMT_B200(get_config(version, device='cpu'))
+    assert [[n, list(p.shape)] for n, p in m.named_parameters()] == man['params']
+    assert [[n, list(b.shape)] for n, b in m.named_buffers()] == man['buffers']
+    # strict load of a DataParallel-style ('module.'-prefixed) checkpoint works on the wrapped module (utils.py:15-19)
+    sd = {'module.' + k: v for k, v in m.state_dict().items()}
+    torch.nn.DataParallel(m).load_state_dict(sd, strict=True)
+
+
+def test_unsupported_config_is_rejected():
+    from diffspectra_b200.config import get_config
+    from diffspectra_b200.model import DMT_B200
+    cfg = get_config('ir', device='cpu')
+    cfg.model.nf = 128
+    with pytest.raises(ValueError):
+        DMT_B200(cfg)
+    cfg = get_config('ir', device='cpu')
+    cfg.data.spectra_version = 'nmr'
+    with pytest.raises(ValueError):
+        DMT_B200(cfg)
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as G
+    G.build()
+    from diffspectra_b200 import _lib as L
+    header = open(os.path.join(ROOT, 'include', 'diffspectra_b200.h')).read()
+    declared = set(re.findall(r'\b(ds_[a-z_0-9]+)\s*\(', header))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert lib.ds_version() >= 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_product_path_fails_loudly_without_gpu():
+    from diffspectra_b200 import DiffSpectraError
+    from diffspectra_b200.config import get_config
+    from diffspectra_b200.model import DMT_B200
+    from oracle import weights as W
+    m = DMT_B200(get_config('ir', device='cpu')).eval()
+    n = torch.tensor([5, 3])
+    nm, em = W.make_masks(n, 5)
+    x, ex = torch.zeros(2, 5, 9), torch.zeros(2, 5, 5, 2)
+    with pytest.raises(DiffSpectraError), torch.no_grad():
+        m(torch.zeros(2), x, nm, em, context=W.synthetic_spectra(2, 'ir'), edge_x=ex, noise_level=torch.zeros(2),
+          cond_x=None, cond_edge_x=None)
+
+
+def test_sampler_rejects_unsupported_modes():
+    from diffspectra_b200.noise_schedule import NoiseScheduleVP
+    from diffspectra_b200.sampling import AncestralSampler
+    ns = NoiseScheduleVP('cosine')
+    ts = torch.linspace(ns.T, 1e-3, 5)
+    with pytest.raises(ValueError):
+        AncestralSampler(ns, ts, False, True, True)
+    with pytest.raises(ValueError):
+        AncestralSampler(ns, ts, True, True, True, cond_process_fn=lambda a, b: (a.clamp(-1, 1), b))
+    with pytest.raises(ValueError):
+        NoiseScheduleVP('discrete')
+    s = AncestralSampler(ns, ts, True, True, True, cond_process_fn=lambda a, b: (a, b))
+    assert s.coefficients().shape == (5, 4)
+
+
+def test_make_masks_equals_reference_loop():
+    from diffspectra_b200.sampling import make_masks
+    from oracle import weights as W
+    n = torch.tensor([3, 29, 1, 17])
+    nm, em = make_masks(n, 'cpu')
+    rn, re = W.make_masks(n)
+    assert torch.equal(nm, rn) and torch.equal(em, re)
