@@ -165,28 +165,45 @@ template <typename AT>
 __device__ __forceinline__ void store2(AT* p, float a, float b);
 template <typename AT>
 __device__ __forceinline__ void store4(AT* p, float a, float b, float c, float d);
-// X[:, 0:64] = RBF_l(|pos_i - pos_j|^2)   (dmt.py:136-138); 8 threads per pair, 8 channels each
+// X[:, 0:64] = RBF_l(|pos_i - pos_j|^2)   (dmt.py:136-138); 8 threads per pair (8 channels each), 4 pairs per thread
+// with the per-channel Gaussian constants hoisted out of the pair loop
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict__ pos, const float* __restrict__ ada, int l,
                                              const float* __restrict__ means, const float* __restrict__ stds,
                                              AT* __restrict__ X) {
-  const int p = blockIdx.x * 32 + (threadIdx.x >> 3), k0 = (threadIdx.x & 7) * 8;
-  if (p >= plan.Mp) return;
-  int mol, i, j;
-  unpack_pair(plan.pair_info[p], mol, i, j);
-  const int base = plan.noff[mol];
-  const float* pi = pos + static_cast<size_t>(base + i) * 3;
-  const float* pj = pos + static_cast<size_t>(base + j) * 3;
-  const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
-  const float r2 = dx * dx + dy * dy + dz * dz;
-  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_RBF;
-  const float x = r2 * (ar[0] + 1.0f) + ar[1];
-  float v[8];
+  const int k0 = (threadIdx.x & 7) * 8;
+  float mean[8], sd[8], coef[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = rbf_value<kFast>(x, k0 + k, means, stds);
-  AT* o = X + static_cast<size_t>(p) * 128 + k0;
-  store4<AT>(o, v[0], v[1], v[2], v[3]);
-  store4<AT>(o + 4, v[4], v[5], v[6], v[7]);
+  for (int k = 0; k < 8; ++k) {
+    const int kk = k0 + k;
+    mean[k] = kk ? means[kk - 1] : 0.f;
+    sd[k] = kk ? fabsf(stds[kk - 1]) + 1e-5f : 1.f;
+    coef[k] = 2.5066272160016134f * sd[k];       // (2*3.14159)**0.5 * std
+  }
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int p = (blockIdx.x * 4 + it) * 32 + (threadIdx.x >> 3);
+    if (p >= plan.Mp) return;
+    int mol, i, j;
+    unpack_pair(plan.pair_info[p], mol, i, j);
+    const int base = plan.noff[mol];
+    const float* pi = pos + static_cast<size_t>(base + i) * 3;
+    const float* pj = pos + static_cast<size_t>(base + j) * 3;
+    const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_RBF;
+    const float x = r2 * (ar[0] + 1.0f) + ar[1];
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float tt = (x - mean[k]) / sd[k];
+      v[k] = act_exp<kFast>(-0.5f * (tt * tt)) / coef[k];
+    }
+    if (k0 == 0) v[0] = x;
+    AT* o = X + static_cast<size_t>(p) * 128 + k0;
+    store4<AT>(o, v[0], v[1], v[2], v[3]);
+    store4<AT>(o + 4, v[4], v[5], v[6], v[7]);
+  }
 }
 
 // 64-wide LayerNorm + modulate, one warp per row, lane owns channels (2*lane, 2*lane+1)
@@ -303,186 +320,127 @@ __global__ void __launch_bounds__(256) k_node_ln1(Plan plan, const float* __rest
   store8<AT>(hh + static_cast<size_t>(m) * 256, lane, v);
 }
 
-// TransMixLayer (layers.py:131-186): one CTA per TARGET atom c; sources r != c of the same molecule.
-//   logits[r, 0:2]  = adjacency heads (1 or -1e10), logits[r, 2+h] = sum_d q[c,h,d] k[r,h,d] e0[(r,c),h,d] / 4
-//   alpha = softmax over r (max-subtracted, denominator + 1e-16);  hn[c, h, :] = sum_r alpha v[r,h,:] e1[(r,c),h,:]
-template <typename AT, bool kFast>
-__global__ void __launch_bounds__(256) k_attention(Plan plan, const float* __restrict__ qkv, const AT* __restrict__ e01,
-                                                   const uint8_t* __restrict__ pflags, float* __restrict__ hn,
-                                                   AT* __restrict__ hnb) {
-  __shared__ float sprod[16][QK_DIM + 1];
-  __shared__ float slog[MAX_ATOMS][N_HEADS];
-  __shared__ int srow[MAX_ATOMS];   // pair row of (c, r)
-  const int m = blockIdx.x;
+// TransMixLayer (layers.py:131-186), one CTA per (molecule, group of ATT_G TARGET atoms); sources = all other
+// atoms of the molecule.  ~25 KB of shared memory per CTA (q rows of the group, logits / softmax weights), so
+// several CTAs are resident per SM; k / v rows and the e0|e1 pair rows are streamed through L1 with 32/64-bit
+// loads; per-target messages accumulate in registers (thread t <-> value channel t).
+constexpr int ATT_G = 8;
+__device__ __forceinline__ float2 ld_pair2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld_pair2(const bf16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename AT, bool kFast, int MAXN>
+__global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, const float* __restrict__ qkv,
+                                                       const AT* __restrict__ e01, const uint8_t* __restrict__ pflags,
+                                                       float* __restrict__ hn, AT* __restrict__ hnb) {
+  __shared__ __align__(16) float sq[ATT_G][256];
+  __shared__ float slog[ATT_G][MAXN][N_HEADS];
+  __shared__ int srow[ATT_G][MAXN];
+  const int mol = blockIdx.x / ngrp, j0 = (blockIdx.x % ngrp) * ATT_G;
+  const int n = plan.n_atoms[mol];
+  if (j0 >= n) return;
   const int t = threadIdx.x;
-  const uint32_t info = plan.node_info[m];
-  const int mol = info >> 6, c = info & 63;
-  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
-  if (t < n) srow[t] = (t == c) ? -1 : pbase + (t < c ? pair_index(n, t, c) : pair_index(n, c, t));
-  const float qc = (t < QK_DIM) ? qkv[static_cast<size_t>(m) * QKV_LD + t] : 0.f;
+  const int base = plan.noff[mol], pbase = plan.poff[mol];
+  const int gsz = min(ATT_G, n - j0);
+  for (int idx = t; idx < gsz * 64; idx += 256) {     // q rows of the targets (252 floats, padded to 256)
+    const int jl = idx >> 6, c4 = idx & 63;
+    *reinterpret_cast<float4*>(&sq[jl][c4 * 4]) =
+        *reinterpret_cast<const float4*>(qkv + static_cast<size_t>(base + j0 + jl) * QKV_LD + c4 * 4);
+  }
+  const int safe_row = min(pbase, max(plan.Mp - 1, 0));     // any valid row: used with weight 0
+  for (int idx = t; idx < ATT_G * n; idx += 256) {
+    const int jl = idx / n, i = idx - jl * n, j = j0 + jl;
+    srow[jl][i] = (jl >= gsz || i == j) ? -1 : pbase + (i < j ? pair_index(n, i, j) : pair_index(n, j, i));
+  }
+  for (int idx = t; idx < (ATT_G - gsz) * n * N_HEADS; idx += 256)    // unused target slots contribute nothing
+    (&slog[gsz][0][0])[(idx / (n * N_HEADS)) * MAXN * N_HEADS + idx % (n * N_HEADS)] = 0.f;
   __syncthreads();
-
-  for (int r0 = 0; r0 < n; r0 += 16) {
-    if (t < QK_DIM) {
-#pragma unroll 4
-      for (int rr = 0; rr < 16; ++rr) {
-        const int r = r0 + rr;
-        float pr = 0.f;
-        if (r < n && r != c) {
-          const float kv = qkv[static_cast<size_t>(base + r) * QKV_LD + 256 + t];
-          const float ev = to_f32(e01[static_cast<size_t>(srow[r]) * E01_LD + t]);
-          pr = qc * kv * ev;
-        }
-        sprod[rr][t] = pr;
-      }
-    }
-    __syncthreads();
-    {
-      const int rr = t >> 4, hh = t & 15;
-      const int r = r0 + rr;
-      if (r < n && r != c) {
-        float lg;
-        if (hh < N_SUB) {
-          float s = 0.f;
-#pragma unroll
-          for (int d = 0; d < C_SUB; ++d) s += sprod[rr][hh * C_SUB + d];
-          lg = s * 0.25f;                       // 1/sqrt(out_channels = 16)
-          slog[r][2 + hh] = lg;
-        } else {
-          const int bit = hh - N_SUB;           // 0: adj2d, 1: adjsp
-          lg = ((pflags[srow[r]] >> bit) & 1) ? 1.0f : -1e10f;
-          slog[r][bit] = lg;
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  // softmax over sources, one warp per two heads
-  {
-    const int warp = t >> 5, lane = t & 31;
-#pragma unroll
-    for (int hsel = 0; hsel < 2; ++hsel) {
-      const int hh = warp * 2 + hsel;
-      float l0 = -INFINITY, l1 = -INFINITY;
-      const bool v0 = lane < n && lane != c, v1 = (lane + 32) < n && (lane + 32) != c;
-      if (v0) l0 = slog[lane][hh];
-      if (v1) l1 = slog[lane + 32][hh];
-      const float mx = warp_max(fmaxf(l0, l1));
-      const float e0 = v0 ? act_exp<kFast>(l0 - mx) : 0.f;
-      const float e1 = v1 ? act_exp<kFast>(l1 - mx) : 0.f;
-      const float den = warp_sum(e0 + e1) + 1e-16f;
-      if (v0) slog[lane][hh] = e0 / den;
-      if (v1) slog[lane + 32][hh] = e1 / den;
-    }
-  }
-  __syncthreads();
-
-  // messages: thread t <-> value channel t (head t/16)
-  float acc = 0.f;
-  const int hh = t >> 4;
-#pragma unroll 4
-  for (int r = 0; r < n; ++r) {
-    if (r == c) continue;
-    const float vv = qkv[static_cast<size_t>(base + r) * QKV_LD + 512 + t];
-    const float ev = to_f32(e01[static_cast<size_t>(srow[r]) * E01_LD + 256 + t]);
-    acc = fmaf(slog[r][hh] * vv, ev, acc);
-  }
-  hn[static_cast<size_t>(m) * 256 + t] = acc;
-  hnb[static_cast<size_t>(m) * 256 + t] = from_f32<AT>(acc);
-}
-
-// TransMixLayer, one CTA per MOLECULE (n <= 32): q/k/v of the molecule live in shared memory, every pair row of
-// e0|e1 is streamed once per pass and serves both directions (i->j and j->i), logits / softmax weights stay in
-// shared memory, messages are accumulated per value channel without atomics.
-constexpr int ATT_MOL_MAXN = 32;
-__host__ __device__ inline size_t att_mol_smem_bytes(int n) {
-  return (static_cast<size_t>(n) * QKV_LD + static_cast<size_t>(n) * n * N_HEADS + static_cast<size_t>(n) * 256) * 4;
-}
-template <typename AT, bool kFast>
-__global__ void __launch_bounds__(256) k_attention_mol(Plan plan, const float* __restrict__ qkv, const AT* __restrict__ e01,
-                                                       const uint8_t* __restrict__ pflags, float* __restrict__ hn,
-                                                       AT* __restrict__ hnb) {
-  extern __shared__ float att_smem[];
-  const int mol = blockIdx.x, t = threadIdx.x;
-  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
-  const int npairs = n * (n - 1) / 2;
-  float* sq = att_smem;                                   // [n][768]
-  float* slog = sq + static_cast<size_t>(n) * QKV_LD;     // [tgt][src][16]
-  float* shn = slog + static_cast<size_t>(n) * n * N_HEADS;   // [n][256]
-  {
-    const float4* src = reinterpret_cast<const float4*>(qkv + static_cast<size_t>(base) * QKV_LD);
-    float4* dst = reinterpret_cast<float4*>(sq);
-    for (int idx = t; idx < n * (QKV_LD / 4); idx += 256) dst[idx] = src[idx];
-    for (int idx = t; idx < n * 256; idx += 256) shn[idx] = 0.f;
-  }
-  __syncthreads();
-  // pass 1: logits for both directions of every pair
-  for (int item = t; item < npairs * N_HEADS; item += 256) {
-    const int pl = item >> 4, hh = item & 15;
-    const uint32_t info = plan.pair_info[pbase + pl];
-    const int i = (info >> 6) & 63, j = info & 63;
-    float lij, lji;       // lij: source i -> target j
+  // pass 1: logits[jl][i][h] for source i -> target j
+  for (int idx = t; idx < gsz * n * N_HEADS; idx += 256) {
+    const int hh = idx & 15, r = idx >> 4;
+    const int jl = r / n, i = r - jl * n;
+    const int row = srow[jl][i];
+    if (row < 0) continue;
+    float lg;
     if (hh < N_SUB) {
-      const AT* er = e01 + static_cast<size_t>(pbase + pl) * E01_LD + hh * C_SUB;
-      const float* qi = sq + i * QKV_LD + hh * C_SUB;
-      const float* qj = sq + j * QKV_LD + hh * C_SUB;
-      float a = 0.f, b = 0.f;
+      const AT* er = e01 + static_cast<size_t>(row) * E01_LD + hh * C_SUB;
+      const float* kr = qkv + static_cast<size_t>(base + i) * QKV_LD + 256 + hh * C_SUB;
+      const float* qr = &sq[jl][hh * C_SUB];
+      float a = 0.f;
 #pragma unroll
-      for (int d = 0; d < C_SUB; ++d) {
-        const float ev = to_f32(er[d]);
-        a = fmaf(qj[d] * qi[256 + d], ev, a);     // q[target j] * k[source i]
-        b = fmaf(qi[d] * qj[256 + d], ev, b);     // q[target i] * k[source j]
+      for (int d = 0; d < C_SUB; d += 2) {
+        const float2 ev = ld_pair2(er + d);
+        const float2 kv = *reinterpret_cast<const float2*>(kr + d);
+        const float2 qv = *reinterpret_cast<const float2*>(qr + d);
+        a = fmaf(qv.x * kv.x, ev.x, a);
+        a = fmaf(qv.y * kv.y, ev.y, a);
       }
-      lij = a * 0.25f;
-      lji = b * 0.25f;
-      slog[(j * n + i) * N_HEADS + 2 + hh] = lij;
-      slog[(i * n + j) * N_HEADS + 2 + hh] = lji;
+      lg = a * 0.25f;                              // 1 / sqrt(out_channels = 16)
+      slog[jl][i][2 + hh] = lg;
     } else {
-      const int bit = hh - N_SUB;
-      const float v = ((pflags[pbase + pl] >> bit) & 1) ? 1.0f : -1e10f;
-      slog[(j * n + i) * N_HEADS + bit] = v;
-      slog[(i * n + j) * N_HEADS + bit] = v;
+      const int bit = hh - N_SUB;                  // 0: adj2d, 1: adjsp
+      slog[jl][i][bit] = ((pflags[row] >> bit) & 1) ? 1.0f : -1e10f;
     }
   }
   __syncthreads();
-  // softmax over sources for every (target, head)
-  for (int task = t; task < n * N_HEADS; task += 256) {
-    const int tg = task >> 4, hh = task & 15;
-    float* row = slog + static_cast<size_t>(tg) * n * N_HEADS + hh;
-    float mx = -INFINITY;
-    for (int s_ = 0; s_ < n; ++s_)
-      if (s_ != tg) mx = fmaxf(mx, row[s_ * N_HEADS]);
-    float den = 0.f;
-    for (int s_ = 0; s_ < n; ++s_)
-      if (s_ != tg) {
-        const float ex = act_exp<kFast>(row[s_ * N_HEADS] - mx);
-        row[s_ * N_HEADS] = ex;
-        den += ex;
-      }
-    const float inv = 1.0f / (den + 1e-16f);
-    for (int s_ = 0; s_ < n; ++s_)
-      if (s_ != tg) row[s_ * N_HEADS] *= inv;
-  }
-  __syncthreads();
-  // pass 2: messages; thread t owns value channel t of every atom
+  // softmax over sources: warp w <-> target j0 + w, lanes <-> sources
   {
-    const int hh = t >> 4;
-    const AT* e1 = e01 + static_cast<size_t>(pbase) * E01_LD + 256 + t;
-#pragma unroll 4
-    for (int pl = 0; pl < npairs; ++pl) {
-      const uint32_t info = plan.pair_info[pbase + pl];
-      const int i = (info >> 6) & 63, j = info & 63;
-      const float ev = to_f32(e1[static_cast<size_t>(pl) * E01_LD]);
-      const float aij = slog[(j * n + i) * N_HEADS + hh], aji = slog[(i * n + j) * N_HEADS + hh];
-      shn[j * 256 + t] = fmaf(aij * sq[i * QKV_LD + 512 + t], ev, shn[j * 256 + t]);
-      shn[i * 256 + t] = fmaf(aji * sq[j * QKV_LD + 512 + t], ev, shn[i * 256 + t]);
+    const int w = t >> 5, lane = t & 31;
+    if (w < gsz) {
+      const int j = j0 + w;
+#pragma unroll 1
+      for (int hh = 0; hh < N_HEADS; ++hh) {
+        float l[MAXN / 32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < MAXN / 32; ++q) {
+          const int i = lane + 32 * q;
+          l[q] = (i < n && i != j) ? slog[w][i][hh] : -INFINITY;
+          mx = fmaxf(mx, l[q]);
+        }
+        mx = warp_max(mx);
+        float den = 0.f;
+#pragma unroll
+        for (int q = 0; q < MAXN / 32; ++q) {
+          const int i = lane + 32 * q;
+          l[q] = (i < n && i != j) ? act_exp<kFast>(l[q] - mx) : 0.f;
+          den += l[q];
+        }
+        den = warp_sum(den) + 1e-16f;
+#pragma unroll
+        for (int q = 0; q < MAXN / 32; ++q) {
+          const int i = lane + 32 * q;
+          if (i < n) slog[w][i][hh] = l[q] / den;    // 0 for i == j
+        }
+      }
     }
   }
-  for (int a = 0; a < n; ++a) {
-    const float v = shn[a * 256 + t];
-    hn[static_cast<size_t>(base + a) * 256 + t] = v;
-    hnb[static_cast<size_t>(base + a) * 256 + t] = from_f32<AT>(v);
+  __syncthreads();
+  // pass 2: messages, thread t <-> value channel t; branch-free so that the 1 + ATT_G loads of an iteration are
+  // all in flight together (rows of masked slots are redirected to a valid row and carry weight 0)
+  float acc[ATT_G];
+#pragma unroll
+  for (int jl = 0; jl < ATT_G; ++jl) acc[jl] = 0.f;
+  const int hh = t >> 4;
+  const AT* e1 = e01 + 256 + t;
+#pragma unroll 2
+  for (int i = 0; i < n; ++i) {
+    const float vv = qkv[static_cast<size_t>(base + i) * QKV_LD + 512 + t];
+    float ev[ATT_G];
+#pragma unroll
+    for (int jl = 0; jl < ATT_G; ++jl) {
+      const int row = srow[jl][i];
+      ev[jl] = to_f32(e1[static_cast<size_t>(row < 0 ? safe_row : row) * E01_LD]);
+    }
+#pragma unroll
+    for (int jl = 0; jl < ATT_G; ++jl) acc[jl] = fmaf(slog[jl][i][hh] * vv, ev[jl], acc[jl]);
+  }
+#pragma unroll
+  for (int jl = 0; jl < ATT_G; ++jl) {
+    if (jl < gsz) {
+      hn[static_cast<size_t>(base + j0 + jl) * 256 + t] = acc[jl];
+      hnb[static_cast<size_t>(base + j0 + jl) * 256 + t] = from_f32<AT>(acc[jl]);
+    }
   }
 }
 
@@ -583,32 +541,48 @@ __global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const float* __rest
   load8(ab + static_cast<size_t>(m) * 512, lane, a);
   load8(ar + 0, lane, sh);
   load8(ar + 256, lane, sc);
-  size_t d = static_cast<size_t>(2 * pbase) + static_cast<size_t>(r) * (n - 1);
-  for (int c = 0; c < n; ++c) {
-    if (c == r) continue;
-    const int p = pbase + (r < c ? pair_index(n, r, c) : pair_index(n, c, r));
-    float v[8], g[8];
-    load8(ab + static_cast<size_t>(base + c) * 512 + 256, lane, v);
-    load8<AT>(gp + static_cast<size_t>(p) * 256, lane, g);
-    float s = 0.f;
+  const size_t d0 = static_cast<size_t>(2 * pbase) + static_cast<size_t>(r) * (n - 1);
+  // two directed edges per iteration: both rows' loads are in flight before the first reduction
+  for (int cc = 0; cc < n - 1; cc += 2) {
+    const bool two = cc + 1 < n - 1;
+    const int c0 = cc + (cc >= r ? 1 : 0);
+    const int c1 = two ? (cc + 1 + (cc + 1 >= r ? 1 : 0)) : c0;
+    const int p0 = pbase + (r < c0 ? pair_index(n, r, c0) : pair_index(n, c0, r));
+    const int p1 = pbase + (r < c1 ? pair_index(n, r, c1) : pair_index(n, c1, r));
+    float v0[8], v1[8], g0[8], g1[8];
+    load8(ab + static_cast<size_t>(base + c0) * 512 + 256, lane, v0);
+    load8(ab + static_cast<size_t>(base + c1) * 512 + 256, lane, v1);
+    load8<AT>(gp + static_cast<size_t>(p0) * 256, lane, g0);
+    load8<AT>(gp + static_cast<size_t>(p1) * 256, lane, g1);
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      v[k] = (a[k] + v[k]) + g[k];
-      s += v[k];
+      v0[k] = (a[k] + v0[k]) + g0[k];
+      v1[k] = (a[k] + v1[k]) + g1[k];
+      s0 += v0[k];
+      s1 += v1[k];
     }
-    const float mean = warp_sum(s) * (1.0f / 256.0f);
-    float q = 0.f;
+    const float m0 = warp_sum(s0) * (1.0f / 256.0f), m1 = warp_sum(s1) * (1.0f / 256.0f);
+    float q0 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      v[k] -= mean;
-      q += v[k] * v[k];
+      v0[k] -= m0;
+      v1[k] -= m1;
+      q0 += v0[k] * v0[k];
+      q1 += v1[k] * v1[k];
     }
-    const float is = inv_std<kFast>(warp_sum(q) * (1.0f / 256.0f));
+    const float is0 = inv_std<kFast>(warp_sum(q0) * (1.0f / 256.0f)), is1 = inv_std<kFast>(warp_sum(q1) * (1.0f / 256.0f));
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (v[k] * is) * (1.0f + sc[k]) + sh[k];
-    store8<AT>(Z + d * 256, lane, v);
-    if (lane == 0) dflags[d] = pflags[p];
-    ++d;
+    for (int k = 0; k < 8; ++k) {
+      v0[k] = (v0[k] * is0) * (1.0f + sc[k]) + sh[k];
+      v1[k] = (v1[k] * is1) * (1.0f + sc[k]) + sh[k];
+    }
+    store8<AT>(Z + (d0 + cc) * 256, lane, v0);
+    if (lane == 0) dflags[d0 + cc] = pflags[p0];
+    if (two) {
+      store8<AT>(Z + (d0 + cc + 1) * 256, lane, v1);
+      if (lane == 0) dflags[d0 + cc + 1] = pflags[p1];
+    }
   }
 }
 
@@ -786,24 +760,14 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     LAUNCH_CHECK(ctx);
   }
 
-  const int max_n = plan.N;
-  const bool att_mol = max_n <= ATT_MOL_MAXN;
-  const size_t att_smem = att_mol_smem_bytes(max_n);
-  if (att_mol) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      DS_CUDA_CHECK(cudaFuncSetAttribute(k_attention_mol<AT, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(att_mol_smem_bytes(ATT_MOL_MAXN))));
-      attr_set = true;
-    }
-  }
+  const int ngrp = (plan.N + ATT_G - 1) / ATT_G;
   uint8_t* dflags = w.pflags + (Mp > 0 ? Mp : 1);      // adjacency bits per directed edge (source-major order)
 
   for (int l = 0; l < N_LAYERS; ++l) {
     const BlockWeights& bw = pw.blk[l];
     const float* ada_l = w.ada + l * ADA_BLK;
     if (Mp > 0) {
-      k_rbf<AT, kFast><<<cdiv(Mp, 32), 256, 0, s>>>(plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
+      k_rbf<AT, kFast><<<cdiv(Mp, 128), 256, 0, s>>>(plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
       LAUNCH_CHECK(ctx);
       if (kFast && (ctx->fuse_mask & 1)) {
         // edge_emb -> LayerNorm -> modulate fused in the GEMM epilogue
@@ -822,13 +786,12 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     k_node_ln1<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h, w.ada, l, reinterpret_cast<AT*>(w.hh));
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hh, 256, bw.wqkv, 256, bw.bqkv, nullptr, 0, w.qkv, QKV_LD, DT_F32, Mn, QKV_LD, 256, ACT_NONE, s));
-    if (att_mol) {
-      k_attention_mol<AT, kFast><<<B, 256, att_smem, s>>>(plan, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags, w.hn,
-                                                          reinterpret_cast<AT*>(w.hnb));
-    } else {
-      k_attention<AT, kFast><<<Mn, 256, 0, s>>>(plan, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags, w.hn,
-                                                reinterpret_cast<AT*>(w.hnb));
-    }
+    if (plan.N <= 32)
+      k_attention_grp<AT, kFast, 32><<<B * ngrp, 256, 0, s>>>(plan, ngrp, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags,
+                                                              w.hn, reinterpret_cast<AT*>(w.hnb));
+    else
+      k_attention_grp<AT, kFast, 64><<<B * ngrp, 256, 0, s>>>(plan, ngrp, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags,
+                                                              w.hn, reinterpret_cast<AT*>(w.hnb));
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hnb, 256, bw.n2e_w, 256, nullptr, nullptr, 0, w.pn, 64, DT_F32, Mn, 64, 256, ACT_NONE, s));
     // node stream
