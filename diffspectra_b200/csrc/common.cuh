@@ -143,7 +143,7 @@ __device__ __forceinline__ int pair_index(int n, int i, int j) {   // i < j < n,
 }
 
 // ----------------------------------------------------------------------------- GEMM  out = act(A W^T + bias + addmat)
-enum GemmMode { GEMM_STORE = 0, GEMM_LNMOD = 1, GEMM_RESGATE = 2, GEMM_COORD = 3 };
+enum GemmMode { GEMM_STORE = 0, GEMM_LNMOD = 1, GEMM_RESGATE = 2, GEMM_COORD = 3, GEMM_EHEAD = 4 };
 
 struct GemmDesc {
   const void* A = nullptr;      // [M, K] row-major, leading dim lda (elements); dtype a_dtype

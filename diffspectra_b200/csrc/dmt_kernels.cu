@@ -160,11 +160,57 @@ __global__ void __launch_bounds__(256) k_root_pairs(Plan plan, const float* __re
   }
 }
 
-// ----------------------------------------------------------------------------- per-block kernels
 template <typename AT>
 __device__ __forceinline__ void store2(AT* p, float a, float b);
 template <typename AT>
 __device__ __forceinline__ void store4(AT* p, float a, float b, float c, float d);
+// tensor-core path of the root edge embedding: operand row = [RBF_root(r0)(64) | edge_x(2) cond_edge(2) | 0 ...]
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_root_operand(Plan plan, const float* __restrict__ es, const float* __restrict__ cond,
+                                                      const float* __restrict__ cond_e, const float* __restrict__ ada,
+                                                      const int* __restrict__ flags, const float* __restrict__ means,
+                                                      const float* __restrict__ stds, AT* __restrict__ xr) {
+  const int p = blockIdx.x * 32 + (threadIdx.x >> 3), k0 = (threadIdx.x & 7) * 8;
+  if (p >= plan.Mp) return;
+  int mol, i, j;
+  unpack_pair(plan.pair_info[p], mol, i, j);
+  float v[8], u[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v[k] = 0.f; u[k] = 0.f; }
+  if (flags[0] != 0) {
+    const int base = plan.noff[mol];
+    const float* ci = cond + static_cast<size_t>(base + i) * 9;
+    const float* cj = cond + static_cast<size_t>(base + j) * 9;
+    const float dx = ci[0] - cj[0], dy = ci[1] - cj[1], dz = ci[2] - cj[2];
+    const float r0 = dx * dx + dy * dy + dz * dz;
+    const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + ADA_ROOT_RBF;
+    const float x = r0 * (ar[0] + 1.0f) + ar[1];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = rbf_value<kFast>(x, k0 + k, means, stds);
+  }
+  if (k0 == 0) {
+    u[0] = es[p * 2]; u[1] = es[p * 2 + 1];
+    u[2] = cond_e ? cond_e[p * 2] : 0.f; u[3] = cond_e ? cond_e[p * 2 + 1] : 0.f;
+  }
+  AT* o = xr + static_cast<size_t>(p) * 128 + k0;
+  store4<AT>(o, v[0], v[1], v[2], v[3]);
+  store4<AT>(o + 4, v[4], v[5], v[6], v[7]);
+  store4<AT>(o + 64, u[0], u[1], u[2], u[3]);
+  store4<AT>(o + 68, u[4], u[5], u[6], u[7]);
+}
+// dst[:, 0:64] (ld dst_ld) = src[:, 0:64] (ld src_ld), 16 bytes per thread
+template <typename AT>
+__global__ void k_copy64(int rows, const AT* __restrict__ src, int src_ld, AT* __restrict__ dst, int dst_ld) {
+  constexpr int per = 16 / sizeof(AT);
+  constexpr int chunks = 64 / per;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * chunks) return;
+  const int r = idx / chunks, c = (idx % chunks) * per;
+  *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * dst_ld + c) =
+      *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * src_ld + c);
+}
+
+// ----------------------------------------------------------------------------- per-block kernels
 // X[:, 0:64] = RBF_l(|pos_i - pos_j|^2)   (dmt.py:136-138); 8 threads per pair (8 channels each), 4 pairs per thread
 // with the per-channel Gaussian constants hoisted out of the pair loop
 template <typename AT, bool kFast>
@@ -330,7 +376,7 @@ __device__ __forceinline__ float2 ld_pair2(const bf16* p) {
   return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
 }
 template <typename AT, bool kFast, int MAXN>
-__global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, const float* __restrict__ qkv,
+__global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, const AT* __restrict__ qkv,
                                                        const AT* __restrict__ e01, const uint8_t* __restrict__ pflags,
                                                        float* __restrict__ hn, AT* __restrict__ hnb) {
   __shared__ __align__(16) float sq[ATT_G][256];
@@ -342,10 +388,9 @@ __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, cons
   const int t = threadIdx.x;
   const int base = plan.noff[mol], pbase = plan.poff[mol];
   const int gsz = min(ATT_G, n - j0);
-  for (int idx = t; idx < gsz * 64; idx += 256) {     // q rows of the targets (252 floats, padded to 256)
+  for (int idx = t; idx < gsz * 64; idx += 256) {     // q rows of the targets (252 values, padded to 256)
     const int jl = idx >> 6, c4 = idx & 63;
-    *reinterpret_cast<float4*>(&sq[jl][c4 * 4]) =
-        *reinterpret_cast<const float4*>(qkv + static_cast<size_t>(base + j0 + jl) * QKV_LD + c4 * 4);
+    *reinterpret_cast<float4*>(&sq[jl][c4 * 4]) = load4<AT>(qkv + static_cast<size_t>(base + j0 + jl) * QKV_LD + c4 * 4);
   }
   const int safe_row = min(pbase, max(plan.Mp - 1, 0));     // any valid row: used with weight 0
   for (int idx = t; idx < ATT_G * n; idx += 256) {
@@ -364,13 +409,13 @@ __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, cons
     float lg;
     if (hh < N_SUB) {
       const AT* er = e01 + static_cast<size_t>(row) * E01_LD + hh * C_SUB;
-      const float* kr = qkv + static_cast<size_t>(base + i) * QKV_LD + 256 + hh * C_SUB;
+      const AT* kr = qkv + static_cast<size_t>(base + i) * QKV_LD + 256 + hh * C_SUB;
       const float* qr = &sq[jl][hh * C_SUB];
       float a = 0.f;
 #pragma unroll
       for (int d = 0; d < C_SUB; d += 2) {
         const float2 ev = ld_pair2(er + d);
-        const float2 kv = *reinterpret_cast<const float2*>(kr + d);
+        const float2 kv = ld_pair2(kr + d);
         const float2 qv = *reinterpret_cast<const float2*>(qr + d);
         a = fmaf(qv.x * kv.x, ev.x, a);
         a = fmaf(qv.y * kv.y, ev.y, a);
@@ -425,7 +470,7 @@ __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, cons
   const AT* e1 = e01 + 256 + t;
 #pragma unroll 2
   for (int i = 0; i < n; ++i) {
-    const float vv = qkv[static_cast<size_t>(base + i) * QKV_LD + 512 + t];
+    const float vv = to_f32(qkv[static_cast<size_t>(base + i) * QKV_LD + 512 + t]);
     float ev[ATT_G];
 #pragma unroll
     for (int jl = 0; jl < ATT_G; ++jl) {
@@ -528,7 +573,7 @@ __global__ void __launch_bounds__(256) k_edge_update2(Plan plan, const float* __
 // the h_r part of input_lin stays in registers, the h_c rows of the molecule come from L1.
 // Also emits the adjacency bits per directed edge for the coordinate head.
 template <typename AT, bool kFast>
-__global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const float* __restrict__ ab, const AT* __restrict__ gp,
+__global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const AT* __restrict__ ab, const AT* __restrict__ gp,
                                                   const float* __restrict__ ada, int l, const uint8_t* __restrict__ pflags,
                                                   AT* __restrict__ Z, uint8_t* __restrict__ dflags) {
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -538,7 +583,7 @@ __global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const float* __rest
   const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
   const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_COORD;
   float a[8], sh[8], sc[8];
-  load8(ab + static_cast<size_t>(m) * 512, lane, a);
+  load8<AT>(ab + static_cast<size_t>(m) * 512, lane, a);
   load8(ar + 0, lane, sh);
   load8(ar + 256, lane, sc);
   const size_t d0 = static_cast<size_t>(2 * pbase) + static_cast<size_t>(r) * (n - 1);
@@ -550,8 +595,8 @@ __global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const float* __rest
     const int p0 = pbase + (r < c0 ? pair_index(n, r, c0) : pair_index(n, c0, r));
     const int p1 = pbase + (r < c1 ? pair_index(n, r, c1) : pair_index(n, c1, r));
     float v0[8], v1[8], g0[8], g1[8];
-    load8(ab + static_cast<size_t>(base + c0) * 512 + 256, lane, v0);
-    load8(ab + static_cast<size_t>(base + c1) * 512 + 256, lane, v1);
+    load8<AT>(ab + static_cast<size_t>(base + c0) * 512 + 256, lane, v0);
+    load8<AT>(ab + static_cast<size_t>(base + c1) * 512 + 256, lane, v1);
     load8<AT>(gp + static_cast<size_t>(p0) * 256, lane, g0);
     load8<AT>(gp + static_cast<size_t>(p1) * 256, lane, g1);
     float s0 = 0.f, s1 = 0.f;
@@ -754,10 +799,23 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
   if (Mp > 0) {
     k_root_pair_flags<<<cdiv(Mp, 256), 256, 0, s>>>(plan, cond_x, cond_e, w.pflags, w.flags);
     LAUNCH_CHECK(ctx);
-    k_root_pairs<AT, kFast><<<cdiv(Mp, 32), 256, 0, s>>>(plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means,
-                                                        pw.root_stds, pw.edge_emb_w, pw.edge_emb_b, w.e, X,
-                                                        reinterpret_cast<AT*>(w.ehid));
-    LAUNCH_CHECK(ctx);
+    if (kFast) {
+      AT* xr = reinterpret_cast<AT*>(w.xr);
+      k_root_operand<AT, kFast><<<cdiv(Mp, 32), 256, 0, s>>>(plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means, pw.root_stds, xr);
+      LAUNCH_CHECK(ctx);
+      GemmDesc g;    // e = edge_emb(operand): fp32 stream + bf16 copy into the [dist | e] operand
+      g.A = xr; g.lda = 128; g.W = pw.root_w; g.ldw = 128; g.bias = pw.edge_emb_b; g.out = w.e; g.ldo = 64;
+      g.M = Mp; g.N = 64; g.K = 128; g.a_dtype = DT_BF16; g.out_dtype = DT_F32; g.mode = GEMM_RESGATE;
+      g.out2 = X + 64; g.ldo2 = 128;
+      DS_TRY(gemm_tc_launch(ctx, g, s));
+      k_copy64<AT><<<cdiv(Mp * 8, 256), 256, 0, s>>>(Mp, X + 64, 128, reinterpret_cast<AT*>(w.ehid), 192);
+      LAUNCH_CHECK(ctx);
+    } else {
+      k_root_pairs<AT, kFast><<<cdiv(Mp, 32), 256, 0, s>>>(plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means,
+                                                          pw.root_stds, pw.edge_emb_w, pw.edge_emb_b, w.e, X,
+                                                          reinterpret_cast<AT*>(w.ehid));
+      LAUNCH_CHECK(ctx);
+    }
   }
 
   const int ngrp = (plan.N + ATT_G - 1) / ATT_G;
@@ -785,12 +843,12 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     }
     k_node_ln1<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h, w.ada, l, reinterpret_cast<AT*>(w.hh));
     LAUNCH_CHECK(ctx);
-    DS_TRY(linear(ctx, w.hh, 256, bw.wqkv, 256, bw.bqkv, nullptr, 0, w.qkv, QKV_LD, DT_F32, Mn, QKV_LD, 256, ACT_NONE, s));
+    DS_TRY(linear(ctx, w.hh, 256, bw.wqkv, 256, bw.bqkv, nullptr, 0, w.qkv, QKV_LD, AD, Mn, QKV_LD, 256, ACT_NONE, s));
     if (plan.N <= 32)
-      k_attention_grp<AT, kFast, 32><<<B * ngrp, 256, 0, s>>>(plan, ngrp, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags,
+      k_attention_grp<AT, kFast, 32><<<B * ngrp, 256, 0, s>>>(plan, ngrp, reinterpret_cast<const AT*>(w.qkv), reinterpret_cast<const AT*>(w.e01), w.pflags,
                                                               w.hn, reinterpret_cast<AT*>(w.hnb));
     else
-      k_attention_grp<AT, kFast, 64><<<B * ngrp, 256, 0, s>>>(plan, ngrp, w.qkv, reinterpret_cast<const AT*>(w.e01), w.pflags,
+      k_attention_grp<AT, kFast, 64><<<B * ngrp, 256, 0, s>>>(plan, ngrp, reinterpret_cast<const AT*>(w.qkv), reinterpret_cast<const AT*>(w.e01), w.pflags,
                                                               w.hn, reinterpret_cast<AT*>(w.hnb));
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hnb, 256, bw.n2e_w, 256, nullptr, nullptr, 0, w.pn, 64, DT_F32, Mn, 64, 256, ACT_NONE, s));
@@ -830,8 +888,8 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       }
       // equivariant coordinate update
       DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, s));
-      DS_TRY(linear(ctx, w.hb, 256, bw.wab, 256, bw.bab, nullptr, 0, w.ab, 512, DT_F32, Mn, 512, 256, ACT_NONE, s));
-      k_coord_ln<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.ab, reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
+      DS_TRY(linear(ctx, w.hb, 256, bw.wab, 256, bw.bab, nullptr, 0, w.ab, 512, AD, Mn, 512, 256, ACT_NONE, s));
+      k_coord_ln<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.ab), reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
                                                         reinterpret_cast<AT*>(w.Z), dflags);
       LAUNCH_CHECK(ctx);
       if (kFast && (ctx->fuse_mask & 8)) {
@@ -862,9 +920,16 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
   LAUNCH_CHECK(ctx);
   if (Mp > 0) {
     DS_TRY(linear(ctx, w.ehid, 192, pw.eh0_w, 192, pw.eh0_b, nullptr, 0, w.eh1, 128, AD, Mp, 128, 192, ACT_SILU, s));
-    k_edge_head_out<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.eh1), pw.eh2t_w, pw.eh2_b,
-                                                           pw.eh4_w, pw.eh4_b, pred_e);
-    LAUNCH_CHECK(ctx);
+    if (kFast) {
+      GemmDesc g;   // second + last layers of both edge heads in one tensor-core pass
+      g.A = w.eh1; g.lda = 128; g.W = pw.eh2_bd; g.ldw = 128; g.bias = pw.eh2_b; g.M = Mp; g.N = 64; g.K = 128;
+      g.a_dtype = DT_BF16; g.mode = GEMM_EHEAD; g.wc2 = pw.eh4_wb; g.wdir = pred_e;
+      DS_TRY(gemm_tc_launch(ctx, g, s));
+    } else {
+      k_edge_head_out<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.eh1), pw.eh2t_w, pw.eh2_b,
+                                                             pw.eh4_w, pw.eh4_b, pred_e);
+      LAUNCH_CHECK(ctx);
+    }
   }
   k_pos_nan_flag<<<cdiv(Mn * 3, 256), 256, 0, s>>>(Mn, w.pos, w.flags);
   LAUNCH_CHECK(ctx);
@@ -903,13 +968,13 @@ size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf) 
   w.h1b = a.take(mn * 256 * es);
   w.pos = static_cast<float*>(a.take(mn * 3 * 4));
   w.hh = a.take(mn * 256 * es);
-  w.qkv = static_cast<float*>(a.take(mn * QKV_LD * 4));
+  w.qkv = a.take(mn * QKV_LD * 4);
   w.hn = static_cast<float*>(a.take(mn * 256 * 4));
   w.hnb = a.take(mn * 256 * es);
   w.pn = static_cast<float*>(a.take(mn * 64 * 4));
   w.f1 = a.take(mn * 512 * es);
   w.f2 = static_cast<float*>(a.take(mn * 256 * 4));
-  w.ab = static_cast<float*>(a.take(mn * 512 * 4));
+  w.ab = a.take(mn * 512 * 4);
   w.ahid = a.take(mn * 768 * es);
   w.n1 = a.take(mn * 256 * es);
   w.n2 = a.take(mn * 128 * es);
@@ -924,6 +989,7 @@ size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf) 
   w.gp = a.take(mp * 256 * es);
   w.ehid = a.take(mp * 192 * es);
   w.eh1 = a.take(mp * 128 * es);
+  w.xr = a.take(mp * 128 * es);
   w.pflags = static_cast<uint8_t*>(a.take(mp + md));   // [Mp] per pair + [2Mp] per directed edge
   w.Z = a.take(md * 256 * es);
   w.u1 = a.take(md * 256 * es);

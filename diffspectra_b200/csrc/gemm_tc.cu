@@ -15,6 +15,7 @@
 //   LNMOD    modulate(LayerNorm(acc + bias), shift[mol], scale[mol])    dmt.py:139,149 (edge_emb -> norm1_edge)
 //   RESGATE  resid + gate[mol] * (acc + bias) -> fp32 stream + bf16 copy  dmt.py:162-163,168-169 (FFN residuals)
 //   COORD    mean(tanh(W2 . SiLU(acc + bias)) * [1, adj2d, adjsp])       dmt.py:32-35,45-51 (coord_mlp + heads)
+//   EHEAD    [w_e . SiLU(acc[:32] + b), w_t . SiLU(acc[32:] + b)]          dmt.py:234-247,394 (edge heads, layers 2+4)
 #include "context.cuh"
 #include "ptx_sm100.cuh"
 
@@ -32,7 +33,9 @@ struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kWBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStagingBytes = TMA_OUT ? kEpiWarps * 2 * kStageBox : 0;
+  // per-warp staging: bf16 TMA-store boxes (2 x 4 KB), RESGATE: fp32 in/out tile (2 boxes) + one bf16 box
+  static constexpr int kWarpStaging = (MODE == GEMM_RESGATE) ? 3 * kStageBox : (TMA_OUT ? 2 * kStageBox : 0);
+  static constexpr int kStagingBytes = kEpiWarps * kWarpStaging;
   static constexpr int kAuxBytes = 2 * 256 * 4 /*bias, per group*/ + (MODE == GEMM_COORD ? 256 * 16 : 0) + 256 /*barriers*/;
   static constexpr int kBudget = 220 * 1024 - kStagingBytes - kAuxBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
@@ -58,6 +61,7 @@ struct Epi {
   const float* wc2;     // COORD: [3,256]
   const uint8_t* pflags;
   float* wdir;
+  int out2_present;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -87,6 +91,20 @@ __device__ __forceinline__ void stage_row_bf16(uint8_t* box, int r, const float 
     u.z = pack_bf16(f[c * 8 + 4], f[c * 8 + 5]);
     u.w = pack_bf16(f[c * 8 + 6], f[c * 8 + 7]);
     *reinterpret_cast<uint4*>(box + r * 128 + ((c ^ (r & 7)) << 4)) = u;
+  }
+}
+
+// 32 fp32 (one 128-byte row) of staging row r, SWIZZLE_128B pattern (chunk = 4 floats)
+__device__ __forceinline__ void stage_row_f32(uint8_t* box, int r, const float* f) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(box + r * 128 + ((c ^ (r & 7)) << 4)) = make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
+}
+__device__ __forceinline__ void unstage_row_f32(const uint8_t* box, int r, float* f) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(box + r * 128 + ((c ^ (r & 7)) << 4));
+    f[c * 4] = v.x; f[c * 4 + 1] = v.y; f[c * 4 + 2] = v.z; f[c * 4 + 3] = v.w;
   }
 }
 
@@ -135,7 +153,8 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, float (&f)[CH]) {
 template <int BN, int MODE, bool TMA_OUT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmO, Epi ep, int M, int N, int K) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmF, Epi ep, int M, int N, int K) {
   using C = Cfg<BN, MODE, TMA_OUT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -149,7 +168,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tfull_bar = bars + 2 * C::kStages;
   uint64_t* tempty_bar = bars + 2 * C::kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+  uint64_t* rbar = bars + 2 * C::kStages + 4;         // [8] RESGATE: residual tile landed (one per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -170,6 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], 128);
     }
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&rbar[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 9) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -235,7 +256,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int g = warp >> 2, wq = warp & 3;
     const int gtid = threadIdx.x & 127;
     float* gb = sbias + g * 256;
-    uint8_t* my_stage = staging + (TMA_OUT ? warp * 2 * kStageBox : 0);
+    uint8_t* my_stage = staging + warp * C::kWarpStaging;
+    uint32_t rphase = 0;
     int sb = 0;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -323,38 +345,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         sb ^= 1;
       } else if constexpr (MODE == GEMM_RESGATE) {
-        const uint32_t mol = row_ok ? (ep.row_info[row] >> ep.info_shift) : 0u;
-        const float* gr = ep.ada + static_cast<size_t>(mol) * ADA_LD + ep.off_a;
+        // out = resid + gate[mol] * (acc + bias): residual tile in via TMA (issued before the accumulator wait),
+        // fp32 stream and bf16 copy out via TMA stores; resid == null (tmR unused): plain acc + bias.
+        const bool active = m0 + wq * 32 < M;
+        const bool has_res = ep.resid != nullptr;
+        const uint32_t mol = (row_ok && has_res) ? (ep.row_info[row] >> ep.info_shift) : 0u;
+        const float* gr = has_res ? ep.ada + static_cast<size_t>(mol) * ADA_LD + ep.off_a : nullptr;
+        uint8_t* fbox = my_stage;                    // two fp32 boxes (cols 0-31, 32-63 of the chunk)
+        uint8_t* bbox = my_stage + 2 * kStageBox;    // one bf16 box
 #pragma unroll 1
         for (int c = 0; c < BN; c += 64) {
+          if (active && has_res) {
+            if (lane == 0) {
+              tma_store_wait_read<0>();              // previous stores have finished reading the staging boxes
+              ptx::mbar_arrive_expect_tx(&rbar[warp], 2 * kStageBox);
+              ptx::tma_load_2d(fbox, &tmR, &rbar[warp], n0 + c, m0 + wq * 32);
+              ptx::tma_load_2d(fbox + kStageBox, &tmR, &rbar[warp], n0 + c + 32, m0 + wq * 32);
+            }
+          } else if (lane == 0) {
+            tma_store_wait_read<0>();
+          }
+          __syncwarp();
           float f[64];
           load_acc<64>(t_addr + c, f);
-          if (row_ok) {
-            const float* rr = ep.resid + static_cast<size_t>(row) * ep.ldres + n0 + c;
-            float* orow = reinterpret_cast<float*>(ep.out) + static_cast<size_t>(row) * ep.ldo + n0 + c;
+          if (active) {
+            if (has_res) {
+              ptx::mbar_wait(&rbar[warp], rphase);
+              rphase ^= 1;
+              float r[64];
+              unstage_row_f32(fbox, lane, r);
+              unstage_row_f32(fbox + kStageBox, lane, r + 32);
 #pragma unroll
-            for (int i = 0; i < 64; i += 4) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rr + i));
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gr + n0 + c + i));
-              f[i + 0] = r4.x + g4.x * (f[i + 0] + gb[c + i + 0]);
-              f[i + 1] = r4.y + g4.y * (f[i + 1] + gb[c + i + 1]);
-              f[i + 2] = r4.z + g4.z * (f[i + 2] + gb[c + i + 2]);
-              f[i + 3] = r4.w + g4.w * (f[i + 3] + gb[c + i + 3]);
-              *reinterpret_cast<float4*>(orow + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+              for (int i = 0; i < 64; i += 4) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gr + n0 + c + i));
+                f[i + 0] = r[i + 0] + g4.x * (f[i + 0] + gb[c + i + 0]);
+                f[i + 1] = r[i + 1] + g4.y * (f[i + 1] + gb[c + i + 1]);
+                f[i + 2] = r[i + 2] + g4.z * (f[i + 2] + gb[c + i + 2]);
+                f[i + 3] = r[i + 3] + g4.w * (f[i + 3] + gb[c + i + 3]);
+              }
+              __syncwarp();                          // every lane has read its residual row
+            } else {
+#pragma unroll
+              for (int i = 0; i < 64; ++i) f[i] += gb[c + i];
+            }
+            stage_row_f32(fbox, lane, f);
+            stage_row_f32(fbox + kStageBox, lane, f + 32);
+            stage_row_bf16(bbox, lane, f);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmF, fbox, n0 + c, m0 + wq * 32);
+              tma_store_2d(&tmF, fbox + kStageBox, n0 + c + 32, m0 + wq * 32);
+              if (ep.out2_present) tma_store_2d(&tmO, bbox, n0 + c, m0 + wq * 32);
+              tma_store_commit();
             }
           }
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-          uint8_t* box = my_stage + sb * kStageBox;
-          stage_row_bf16(box, lane, f);
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (m0 + wq * 32 < M) tma_store_2d(&tmO, box, n0 + c, m0 + wq * 32);
-            tma_store_commit();
-          }
-          sb ^= 1;
         }
+      } else if constexpr (MODE == GEMM_EHEAD) {
+        // BN == N == 64: second layers of edge_exist_mlp | edge_type_mlp (block-diagonal weight), SiLU, then the
+        // two 32 -> 1 output layers as per-row dot products  (dmt.py:234-247,394)
+        float f[64];
+        load_acc<64>(t_addr, f);
+        float s0 = ep.wc2[64], s1 = ep.wc2[65];       // output biases
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s0 = fmaf(act_silu<true>(f[i] + gb[i]), __ldg(ep.wc2 + i), s0);
+          s1 = fmaf(act_silu<true>(f[32 + i] + gb[32 + i]), __ldg(ep.wc2 + 32 + i), s1);
+        }
+        if (row_ok) *reinterpret_cast<float2*>(ep.wdir + static_cast<size_t>(row) * 2) = make_float2(s0, s1);
       } else {   // GEMM_COORD, BN == N == 256
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -379,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty_bar[g]);
     }
-    if (TMA_OUT && lane == 0) tma_store_wait_all();
+    if ((TMA_OUT || MODE == GEMM_RESGATE) && lane == 0) tma_store_wait_all();
   }
 
   ptx::tc_fence_before();
@@ -394,14 +452,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap(DsContext* ctx, CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+int make_tmap(DsContext* ctx, CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols, int box_rows,
+              bool f32 = false) {
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  const int es = f32 ? 4 : 2;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * es};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                  gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DS_CHECK(r == CUDA_SUCCESS, DS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d base=%p", (int)r,
            rows, cols, ld, base);
@@ -416,25 +476,27 @@ int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
     DS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  CUtensorMap tmA, tmW, tmO;
+  CUtensorMap tmA, tmW, tmO, tmR, tmF;
   DS_TRY(make_tmap(ctx, &tmA, g.A, g.M, g.K, g.lda, BK, BM));
   DS_TRY(make_tmap(ctx, &tmW, g.W, g.N, g.K, g.ldw, BK, BN));
-  if (TMA_OUT) {
-    const void* ob = (MODE == GEMM_RESGATE) ? g.out2 : g.out;
-    const int ld = (MODE == GEMM_RESGATE) ? g.ldo2 : g.ldo;
-    DS_TRY(make_tmap(ctx, &tmO, ob, g.M, g.N, ld, 64, 32));
-  } else {
-    tmO = tmA;
+  tmO = tmA; tmR = tmA; tmF = tmA;
+  if (MODE == GEMM_RESGATE) {
+    DS_TRY(make_tmap(ctx, &tmF, g.out, g.M, g.N, g.ldo, 32, 32, true));
+    if (g.resid) DS_TRY(make_tmap(ctx, &tmR, g.resid, g.M, g.N, g.ldres, 32, 32, true));
+    if (g.out2) DS_TRY(make_tmap(ctx, &tmO, g.out2, g.M, g.N, g.ldo2, 64, 32));
+  } else if (TMA_OUT) {
+    DS_TRY(make_tmap(ctx, &tmO, g.out, g.M, g.N, g.ldo, 64, 32));
   }
   Epi ep;
   ep.bias = g.bias; ep.addmat = g.addmat; ep.out = g.out; ep.ldo = g.ldo; ep.ldadd = g.ldadd;
   ep.out_dtype = g.out_dtype; ep.act = g.act;
   ep.row_info = g.row_info; ep.info_shift = g.info_shift; ep.ada = g.ada; ep.off_a = g.off_a; ep.off_b = g.off_b;
   ep.resid = g.resid; ep.ldres = g.ldres; ep.wc2 = g.wc2; ep.pflags = g.pflags; ep.wdir = g.wdir;
+  ep.out2_present = g.out2 != nullptr;
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  gemm_tc_kernel<BN, MODE, TMA_OUT><<<grid, kThreads, C::kSmemBytes, s>>>(tmA, tmW, tmO, ep, g.M, g.N, g.K);
+  gemm_tc_kernel<BN, MODE, TMA_OUT><<<grid, kThreads, C::kSmemBytes, s>>>(tmA, tmW, tmO, tmR, tmF, ep, g.M, g.N, g.K);
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;
   return DS_OK;
@@ -462,9 +524,13 @@ int gemm_tc_launch(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
       DS_CHECK(g.N == 64 && g.out_dtype == DT_BF16, DS_ERR_INVALID, "gemm_tc LNMOD: N must be 64, bf16 out");
       return launch_cfg<64, GEMM_LNMOD, true>(ctx, g, s);
     case GEMM_RESGATE:
-      DS_CHECK((g.N == 64 || g.N == 256) && g.out_dtype == DT_F32 && g.out2 != nullptr, DS_ERR_INVALID, "gemm_tc RESGATE: N in {64,256}");
+      DS_CHECK((g.N == 64 || g.N == 256) && g.out_dtype == DT_F32, DS_ERR_INVALID, "gemm_tc RESGATE: N in {64,256}, fp32 out");
+      DS_CHECK((g.ldo % 4) == 0 && (reinterpret_cast<uintptr_t>(g.out) & 15) == 0, DS_ERR_INVALID, "gemm_tc RESGATE: out alignment");
       if (g.N == 64) return launch_cfg<64, GEMM_RESGATE, true>(ctx, g, s);
       return launch_cfg<256, GEMM_RESGATE, true>(ctx, g, s);
+    case GEMM_EHEAD:
+      DS_CHECK(g.N == 64 && g.wc2 && g.wdir, DS_ERR_INVALID, "gemm_tc EHEAD: N must be 64");
+      return launch_cfg<64, GEMM_EHEAD, false>(ctx, g, s);
     case GEMM_COORD:
       DS_CHECK(g.N == 256, DS_ERR_INVALID, "gemm_tc COORD: N must be 256");
       return launch_cfg<256, GEMM_COORD, false>(ctx, g, s);

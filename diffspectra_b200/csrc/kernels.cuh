@@ -59,6 +59,9 @@ struct PackedWeights {
   const float* eh2_b;                      // [2][32]
   const float* eh4_w;                      // [2][32]
   const float* eh4_b;                      // [2]
+  const void* eh2_bd;                      // act [64,128] block-diagonal second layers (tensor-core path)
+  const float* eh4_wb;                     // [66] = w4 exist | w4 type | b4 exist, b4 type
+  const void* root_w;                      // act [64,128] root edge_emb for operand [d0 | edge_x cond_edge | 0]
   // SpecFormer
   int n_spec = 0;                          // number of spectra used (1 or 3)
   int spec_type[3];                        // 0 uv, 1 ir, 2 raman
@@ -96,13 +99,13 @@ struct DenoiseWs {      // scratch of one denoiser call on a plan (sizes in elem
   void* h1b;            // act
   float* pos;           // [Mn,3]
   void* hh;             // act [Mn,256]
-  float* qkv;           // [Mn,768]
+  void* qkv;            // [Mn,768] fp32 (validation) / bf16
   float* hn;            // [Mn,256]
   void* hnb;            // act
   float* pn;            // [Mn,64]
   void* f1;             // act [Mn,512]
   float* f2;            // [Mn,256]
-  float* ab;            // [Mn,512]
+  void* ab;             // [Mn,512] fp32 (validation) / bf16
   void* ahid;           // act [Mn,768]
   void* n1;             // act [Mn,256]
   void* n2;             // act [Mn,128]
@@ -117,6 +120,7 @@ struct DenoiseWs {      // scratch of one denoiser call on a plan (sizes in elem
   void* gp;             // act [Mp,256]
   void* ehid;           // act [Mp,192]
   void* eh1;            // act [Mp,128]
+  void* xr;             // act [Mp,128] root edge-embedding operand
   uint8_t* pflags;      // [Mp]
   void* Z;              // act [2Mp,256]
   void* u1;             // act [2Mp,256]

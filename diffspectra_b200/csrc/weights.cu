@@ -73,6 +73,13 @@ int build(Packer& P, PackedWeights& pw) {
   pw.node_emb_b = P.vec("node_emb.bias", 256);
   pw.edge_emb_w = P.vec("edge_emb.weight", 64 * 68);
   pw.edge_emb_b = P.vec("edge_emb.bias", 64);
+  {   // tensor-core form of the root edge embedding: operand columns [d0(64) | edge_x(2) cond_edge(2) | 0...]
+    const float* we = P.get("edge_emb.weight");   // [64,68], input order [edge_x(2) | cond_edge(2) | d0(64)]
+    void* wr = P.alloc_act(64 * 128);
+    P.copy(we ? we + 4 : nullptr, 68, wr, 0, 128, 64, 64, true);
+    P.copy(we, 68, wr, 64, 128, 64, 4, true);
+    pw.root_w = wr;
+  }
   pw.root_means = P.vec("dist_layer.means.weight", 63);
   pw.root_stds = P.vec("dist_layer.stds.weight", 63);
   pw.tm_freq = P.vec("time_mlp.0.weights", 8);
@@ -188,6 +195,17 @@ int build(Packer& P, PackedWeights& pw) {
     pw.eh2_b = b2;
     pw.eh4_w = w4;
     pw.eh4_b = b4;
+    // tensor-core form of the same layers: block-diagonal [64,128] second layer, [w4_exist | w4_type | b4] vector
+    void* wbd = P.alloc_act(64 * 128);
+    float* w4b = P.alloc_f32(66);
+    P.copy(P.get("edge_exist_mlp.2.weight"), 64, wbd, 0, 128, 32, 64, true);
+    P.copy(P.get("edge_type_mlp.2.weight"), 64, wbd, 32 * 128 + 64, 128, 32, 64, true);
+    P.copy(P.get("edge_exist_mlp.4.weight"), 32, w4b, 0, 32, 1, 32, false);
+    P.copy(P.get("edge_type_mlp.4.weight"), 32, w4b, 32, 32, 1, 32, false);
+    P.copy(P.get("edge_exist_mlp.4.bias"), 1, w4b, 64, 1, 1, 1, false);
+    P.copy(P.get("edge_type_mlp.4.bias"), 1, w4b, 65, 1, 1, 1, false);
+    pw.eh2_bd = wbd;
+    pw.eh4_wb = w4b;
   }
 
   // ---------------- SpecFormer (models/specformer.py) ----------------
