@@ -9,12 +9,14 @@
 #include <stdio.h>
 
 // ----------------------------------------------------------------------------- error codes (mirrored in the header)
+#ifndef DS_OK
 #define DS_OK 0
-#define DS_ERR_INVALID -1
-#define DS_ERR_CUDA -2
-#define DS_ERR_MISSING_PARAM -3
-#define DS_ERR_UNSUPPORTED -4
-#define DS_ERR_WORKSPACE -5
+#define DS_ERR_INVALID (-1)
+#define DS_ERR_CUDA (-2)
+#define DS_ERR_MISSING_PARAM (-3)
+#define DS_ERR_UNSUPPORTED (-4)
+#define DS_ERR_WORKSPACE (-5)
+#endif
 
 #define DS_CUDA_CHECK(expr)                                                                       \
   do {                                                                                            \

@@ -20,6 +20,11 @@ __device__ __forceinline__ float inv_std(float var) {
   return kFast ? rsqrtf(var + kLnEps) : 1.0f / sqrtf(var + kLnEps);
 }
 
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ void unpack_pair(uint32_t info, int& mol, int& i, int& j) {
   mol = info >> 12;
   i = (info >> 6) & 63;
@@ -218,13 +223,14 @@ __global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict_
                                              const float* __restrict__ means, const float* __restrict__ stds,
                                              AT* __restrict__ X) {
   const int k0 = (threadIdx.x & 7) * 8;
-  float mean[8], sd[8], coef[8];
+  float mean[8], sd[8], coef[8];     // fast mode: sd / coef hold the RECIPROCALS (2 multiplies instead of 2 divisions)
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int kk = k0 + k;
     mean[k] = kk ? means[kk - 1] : 0.f;
     sd[k] = kk ? fabsf(stds[kk - 1]) + 1e-5f : 1.f;
     coef[k] = 2.5066272160016134f * sd[k];       // (2*3.14159)**0.5 * std
+    if (kFast) { sd[k] = 1.0f / sd[k]; coef[k] = 1.0f / coef[k]; }
   }
 #pragma unroll 1
   for (int it = 0; it < 4; ++it) {
@@ -242,8 +248,13 @@ __global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict_
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float tt = (x - mean[k]) / sd[k];
-      v[k] = act_exp<kFast>(-0.5f * (tt * tt)) / coef[k];
+      if (kFast) {
+        const float tt = (x - mean[k]) * sd[k];
+        v[k] = exp2f(-0.72134752044448170368f * (tt * tt)) * coef[k];     // exp(-0.5 t^2) = 2^(-0.5 log2(e) t^2)
+      } else {
+        const float tt = (x - mean[k]) / sd[k];
+        v[k] = expf(-0.5f * (tt * tt)) / coef[k];
+      }
     }
     if (k0 == 0) v[0] = x;
     AT* o = X + static_cast<size_t>(p) * 128 + k0;
@@ -392,13 +403,10 @@ __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, cons
     const int jl = idx >> 6, c4 = idx & 63;
     *reinterpret_cast<float4*>(&sq[jl][c4 * 4]) = load4<AT>(qkv + static_cast<size_t>(base + j0 + jl) * QKV_LD + c4 * 4);
   }
-  const int safe_row = min(pbase, max(plan.Mp - 1, 0));     // any valid row: used with weight 0
-  for (int idx = t; idx < ATT_G * n; idx += 256) {
+  for (int idx = t; idx < gsz * n; idx += 256) {
     const int jl = idx / n, i = idx - jl * n, j = j0 + jl;
-    srow[jl][i] = (jl >= gsz || i == j) ? -1 : pbase + (i < j ? pair_index(n, i, j) : pair_index(n, j, i));
+    srow[jl][i] = (i == j) ? -1 : pbase + (i < j ? pair_index(n, i, j) : pair_index(n, j, i));
   }
-  for (int idx = t; idx < (ATT_G - gsz) * n * N_HEADS; idx += 256)    // unused target slots contribute nothing
-    (&slog[gsz][0][0])[(idx / (n * N_HEADS)) * MAXN * N_HEADS + idx % (n * N_HEADS)] = 0.f;
   __syncthreads();
   // pass 1: logits[jl][i][h] for source i -> target j
   for (int idx = t; idx < gsz * n * N_HEADS; idx += 256) {
@@ -428,64 +436,51 @@ __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, cons
     }
   }
   __syncthreads();
-  // softmax over sources: warp w <-> target j0 + w, lanes <-> sources
-  {
-    const int w = t >> 5, lane = t & 31;
-    if (w < gsz) {
-      const int j = j0 + w;
-#pragma unroll 1
-      for (int hh = 0; hh < N_HEADS; ++hh) {
-        float l[MAXN / 32];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int q = 0; q < MAXN / 32; ++q) {
-          const int i = lane + 32 * q;
-          l[q] = (i < n && i != j) ? slog[w][i][hh] : -INFINITY;
-          mx = fmaxf(mx, l[q]);
-        }
-        mx = warp_max(mx);
-        float den = 0.f;
-#pragma unroll
-        for (int q = 0; q < MAXN / 32; ++q) {
-          const int i = lane + 32 * q;
-          l[q] = (i < n && i != j) ? act_exp<kFast>(l[q] - mx) : 0.f;
-          den += l[q];
-        }
-        den = warp_sum(den) + 1e-16f;
-#pragma unroll
-        for (int q = 0; q < MAXN / 32; ++q) {
-          const int i = lane + 32 * q;
-          if (i < n) slog[w][i][hh] = l[q] / den;    // 0 for i == j
-        }
-      }
+  // softmax over sources: one thread per (target, head), serial over sources (no shuffles, every lane busy)
+  if (t < gsz * N_HEADS) {
+    const int jl = t >> 4, hh = t & 15, j = j0 + jl;
+    float mx = -INFINITY;
+    for (int i = 0; i < n; ++i)
+      if (i != j) mx = fmaxf(mx, slog[jl][i][hh]);
+    float den = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float ex = (i != j) ? act_exp<kFast>(slog[jl][i][hh] - mx) : 0.f;
+      slog[jl][i][hh] = ex;
+      den += ex;
     }
+    const float inv = 1.0f / (den + 1e-16f);
+    for (int i = 0; i < n; ++i) slog[jl][i][hh] *= inv;
   }
   __syncthreads();
-  // pass 2: messages, thread t <-> value channel t; branch-free so that the 1 + ATT_G loads of an iteration are
-  // all in flight together (rows of masked slots are redirected to a valid row and carry weight 0)
-  float acc[ATT_G];
+  // pass 2: messages; warp w <-> target j0 + w, lane <-> 8 value channels (one head per 2 lanes):
+  // hn[j, c] = sum_i alpha[i->j, head(c)] * v[i, c] * e1[(i,j), c]
+  {
+    const int w = t >> 5, lane = t & 31;
+    if (w >= gsz) return;
+    const int j = j0 + w, hh = lane >> 1;
+    float acc[8];
 #pragma unroll
-  for (int jl = 0; jl < ATT_G; ++jl) acc[jl] = 0.f;
-  const int hh = t >> 4;
-  const AT* e1 = e01 + 256 + t;
-#pragma unroll 2
-  for (int i = 0; i < n; ++i) {
-    const float vv = to_f32(qkv[static_cast<size_t>(base + i) * QKV_LD + 512 + t]);
-    float ev[ATT_G];
-#pragma unroll
-    for (int jl = 0; jl < ATT_G; ++jl) {
-      const int row = srow[jl][i];
-      ev[jl] = to_f32(e1[static_cast<size_t>(row < 0 ? safe_row : row) * E01_LD]);
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const AT* vbase = qkv + static_cast<size_t>(base) * QKV_LD + 512 + lane * 8;
+    const AT* ebase = e01 + 256 + lane * 8;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+      if (i == j) continue;
+      const float al = slog[w][i][hh];
+      const float4 v0 = load4<AT>(vbase + static_cast<size_t>(i) * QKV_LD), v1 = load4<AT>(vbase + static_cast<size_t>(i) * QKV_LD + 4);
+      const AT* er = ebase + static_cast<size_t>(srow[w][i]) * E01_LD;
+      const float4 e0 = load4<AT>(er), e1 = load4<AT>(er + 4);
+      acc[0] = fmaf(al * v0.x, e0.x, acc[0]); acc[1] = fmaf(al * v0.y, e0.y, acc[1]);
+      acc[2] = fmaf(al * v0.z, e0.z, acc[2]); acc[3] = fmaf(al * v0.w, e0.w, acc[3]);
+      acc[4] = fmaf(al * v1.x, e1.x, acc[4]); acc[5] = fmaf(al * v1.y, e1.y, acc[5]);
+      acc[6] = fmaf(al * v1.z, e1.z, acc[6]); acc[7] = fmaf(al * v1.w, e1.w, acc[7]);
     }
-#pragma unroll
-    for (int jl = 0; jl < ATT_G; ++jl) acc[jl] = fmaf(slog[jl][i][hh] * vv, ev[jl], acc[jl]);
-  }
-#pragma unroll
-  for (int jl = 0; jl < ATT_G; ++jl) {
-    if (jl < gsz) {
-      hn[static_cast<size_t>(base + j0 + jl) * 256 + t] = acc[jl];
-      hnb[static_cast<size_t>(base + j0 + jl) * 256 + t] = from_f32<AT>(acc[jl]);
-    }
+    float* ho = hn + static_cast<size_t>(base + j) * 256 + lane * 8;
+    *reinterpret_cast<float4*>(ho) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(ho + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    AT* hb_ = hnb + static_cast<size_t>(base + j) * 256 + lane * 8;
+    store4<AT>(hb_, acc[0], acc[1], acc[2], acc[3]);
+    store4<AT>(hb_ + 4, acc[4], acc[5], acc[6], acc[7]);
   }
 }
 
@@ -529,26 +524,40 @@ __global__ void __launch_bounds__(256) k_node_update2(Plan plan, const float* __
 }
 
 // e1 = modulate(LN(e_in + eg1 * node2edge_lin(hn_i + hn_j)), esh2, esc2)   (dmt.py:156-157,165-167)
+// half a warp per pair (16 lanes x 4 channels): 4-step shuffles serve two rows at once
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_edge_update1(Plan plan, const float* __restrict__ e, const float* __restrict__ pn,
                                                       const float* __restrict__ n2e_b, const float* __restrict__ ada, int l,
                                                       float* __restrict__ e1f, AT* __restrict__ e1b) {
-  const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (p >= plan.Mp) return;
+  const int p = blockIdx.x * 16 + (threadIdx.x >> 4), c0 = (threadIdx.x & 15) * 4;
+  const bool ok = p < plan.Mp;
+  const int pp = ok ? p : plan.Mp - 1;
   int mol, i, j;
-  unpack_pair(plan.pair_info[p], mol, i, j);
+  unpack_pair(plan.pair_info[pp], mol, i, j);
   const int base = plan.noff[mol];
   const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_EDGE;
-  const float2 ev = *reinterpret_cast<const float2*>(e + static_cast<size_t>(p) * 64 + 2 * lane);
-  const float2 pi = *reinterpret_cast<const float2*>(pn + static_cast<size_t>(base + i) * 64 + 2 * lane);
-  const float2 pj = *reinterpret_cast<const float2*>(pn + static_cast<size_t>(base + j) * 64 + 2 * lane);
-  const float2 bb = *reinterpret_cast<const float2*>(n2e_b + 2 * lane);
-  const float2 g = *reinterpret_cast<const float2*>(ar + 128 + 2 * lane);
+  const float4 ev = *reinterpret_cast<const float4*>(e + static_cast<size_t>(pp) * 64 + c0);
+  const float4 pi = *reinterpret_cast<const float4*>(pn + static_cast<size_t>(base + i) * 64 + c0);
+  const float4 pj = *reinterpret_cast<const float4*>(pn + static_cast<size_t>(base + j) * 64 + c0);
+  const float4 bb = *reinterpret_cast<const float4*>(n2e_b + c0);
+  const float4 g = *reinterpret_cast<const float4*>(ar + 128 + c0);
+  const float4 sh = *reinterpret_cast<const float4*>(ar + 192 + c0);
+  const float4 sc = *reinterpret_cast<const float4*>(ar + 256 + c0);
   float v0 = ev.x + g.x * ((pi.x + pj.x) + bb.x);
   float v1 = ev.y + g.y * ((pi.y + pj.y) + bb.y);
-  ln64_mod<kFast>(v0, v1, ar + 192, ar + 256, lane);
-  store2<float>(e1f + static_cast<size_t>(p) * 64 + 2 * lane, v0, v1);
-  store2<AT>(e1b + static_cast<size_t>(p) * 64 + 2 * lane, v0, v1);
+  float v2 = ev.z + g.z * ((pi.z + pj.z) + bb.z);
+  float v3 = ev.w + g.w * ((pi.w + pj.w) + bb.w);
+  const float mean = half_warp_sum((v0 + v1) + (v2 + v3)) * (1.0f / 64.0f);
+  v0 -= mean; v1 -= mean; v2 -= mean; v3 -= mean;
+  const float var = half_warp_sum((v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3)) * (1.0f / 64.0f);
+  const float is = inv_std<kFast>(var);
+  v0 = (v0 * is) * (1.0f + sc.x) + sh.x;
+  v1 = (v1 * is) * (1.0f + sc.y) + sh.y;
+  v2 = (v2 * is) * (1.0f + sc.z) + sh.z;
+  v3 = (v3 * is) * (1.0f + sc.w) + sh.w;
+  if (!ok) return;
+  *reinterpret_cast<float4*>(e1f + static_cast<size_t>(p) * 64 + c0) = make_float4(v0, v1, v2, v3);
+  store4<AT>(e1b + static_cast<size_t>(p) * 64 + c0, v0, v1, v2, v3);
 }
 
 // e = e1 + eg2 * FFN(e1)  (dmt.py:168-169); also refreshes the [dist | e] GEMM operand
@@ -870,7 +879,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     }
     if (Mp > 0) {
       // edge stream
-      k_edge_update1<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
+      k_edge_update1<AT, kFast><<<cdiv(Mp, 16), 256, 0, s>>>(plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
                                                             reinterpret_cast<AT*>(w.e1b));
       LAUNCH_CHECK(ctx);
       DS_TRY(linear(ctx, w.e1b, 64, bw.ff3_w, 64, bw.ff3_b, nullptr, 0, w.f3, 128, AD, Mp, 128, 64, ACT_SILU, s));
