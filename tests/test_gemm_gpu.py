@@ -107,7 +107,7 @@ def _fused_inputs(M, N, K, n_mol, seed):
     return A, W, bias, mol, info, ada
 
 
-@pytest.mark.parametrize('M', [300, 128, 5000])
+@pytest.mark.parametrize('M', [300, 128, 5000, 40000])
 def test_gemm_fused_lnmod(ctx, M):
     N, K = 64, 128
     A, W, bias, mol, info, ada = _fused_inputs(M, N, K, 7, M)
@@ -122,7 +122,7 @@ def test_gemm_fused_lnmod(ctx, M):
     assert (out[M:] == -7).all()
 
 
-@pytest.mark.parametrize('M,N,K', [(300, 64, 128), (1000, 256, 512)])
+@pytest.mark.parametrize('M,N,K', [(300, 64, 128), (1000, 256, 512), (40000, 64, 128)])
 def test_gemm_fused_resgate(ctx, M, N, K):
     A, W, bias, mol, info, ada = _fused_inputs(M, N, K, 5, M + N)
     off = 320
@@ -140,8 +140,9 @@ def test_gemm_fused_resgate(ctx, M, N, K):
     assert (buf2[:, :N] == 0).all()
 
 
-def test_gemm_fused_coord(ctx):
-    M, N, K = 3001, 256, 256
+@pytest.mark.parametrize('M', [3001, 40001])
+def test_gemm_fused_coord(ctx, M):
+    N, K = 256, 256
     A, W, bias, mol, info, ada = _fused_inputs(M, N, K, 5, 3)
     g = torch.Generator(device='cuda').manual_seed(4)
     wc2 = torch.randn(3, 256, device='cuda', generator=g) / 16
@@ -155,3 +156,18 @@ def test_gemm_fused_coord(ctx):
     ref = (u * adj).mean(-1)
     assert (wdir[:M] - ref).abs().max().item() < 5e-3
     assert (wdir[M:] == -7).all()
+
+
+@pytest.mark.parametrize('M,N,K,act', [(40000, 512, 64, L.ACT_TANH), (40000, 256, 128, L.ACT_NONE), (50001, 128, 64, L.ACT_SILU),
+                                       (40000, 16, 64, L.ACT_NONE), (40000, 64, 256, L.ACT_NONE)])
+def test_gemm_tc_many_tiles_per_cta_bf16_out(ctx, M, N, K, act):
+    """Many m-tiles per SM: every persistent CTA walks several output tiles (ring + TMEM stage phases wrap)."""
+    g = torch.Generator(device='cuda').manual_seed(M + N)
+    A = torch.randn(M, K, device='cuda', generator=g).bfloat16()
+    W = (torch.randn(N, K, device='cuda', generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device='cuda', generator=g) * 0.1
+    ref = ACTS[act](A.float() @ W.float().t() + bias)
+    out = torch.full((M + 3, N), -7.0, device='cuda', dtype=torch.bfloat16)
+    run_gemm(ctx, True, A, W, bias, None, out[:M], act, M, N, K)
+    assert (out[:M].float() - ref).abs().max().item() < 3e-2
+    assert (out[M:] == -7).all()
