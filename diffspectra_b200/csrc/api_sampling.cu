@@ -25,9 +25,10 @@ struct CtxFull : DsContext {
 
 inline CtxFull* full(ds_ctx* h) { return reinterpret_cast<CtxFull*>(h); }
 
-// plan blob layout (device, int32): n_atoms[B] | noff[B+1] | poff[B+1] | node_info[Mn_max] | pair_info[Mp_max]
+// plan blob layout (device, int32): n_atoms[B] | noff[B+1] | poff[B+1] | node_info[Mn_max] | pair_info[Mp_max] |
+// dir_info[2*Mp_max] (int4)
 struct PlanLayout {
-  size_t n_atoms, noff, poff, node_info, pair_info, total;
+  size_t n_atoms, noff, poff, node_info, pair_info, dir_info, total;
 };
 PlanLayout plan_layout(int B, int N) {
   PlanLayout L;
@@ -38,6 +39,7 @@ PlanLayout plan_layout(int B, int N) {
   L.poff = o; o = al(o + size_t(B + 1) * 4);
   L.node_info = o; o = al(o + size_t(B) * N * 4);
   L.pair_info = o; o = al(o + size_t(B) * N * (N - 1) / 2 * 4 + 4);
+  L.dir_info = o; o = al(o + size_t(B) * N * (N - 1) * 16 + 16);
   L.total = o;
   return L;
 }
@@ -52,6 +54,7 @@ int make_plan(const void* plan_dev, int B, int N, int Mn, int Mp, Plan* p) {
   p->poff = reinterpret_cast<const int*>(base + L.poff);
   p->node_info = reinterpret_cast<const uint32_t*>(base + L.node_info);
   p->pair_info = reinterpret_cast<const uint32_t*>(base + L.pair_info);
+  p->dir_info = reinterpret_cast<const int4*>(base + L.dir_info);
   return DS_OK;
 }
 
@@ -109,6 +112,7 @@ int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_d
   int* poff = reinterpret_cast<int*>(host.data() + L.poff);
   uint32_t* ni = reinterpret_cast<uint32_t*>(host.data() + L.node_info);
   uint32_t* pi = reinterpret_cast<uint32_t*>(host.data() + L.pair_info);
+  int4* di = reinterpret_cast<int4*>(host.data() + L.dir_info);
   int mn = 0, mp = 0;
   for (int b = 0; b < B; ++b) {
     const int n = n_atoms_host[b];
@@ -120,6 +124,13 @@ int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_d
     int q = mp;
     for (int i = 0; i < n; ++i)
       for (int j = i + 1; j < n; ++j) pi[q++] = (static_cast<uint32_t>(b) << 12) | (i << 6) | j;
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < n; ++c) {
+        if (c == r) continue;
+        const int lo = r < c ? r : c, hi = r < c ? c : r;
+        const int pr = mp + lo * n - (lo * (lo + 1)) / 2 + (hi - lo - 1);
+        di[static_cast<size_t>(2) * mp + static_cast<size_t>(r) * (n - 1) + (c - (c > r ? 1 : 0))] = make_int4(pr, mn + r, mn + c, b);
+      }
     mn += n;
     mp += n * (n - 1) / 2;
   }

@@ -69,7 +69,9 @@ constexpr int ADA_ROOT_RBF = N_LAYERS * ADA_BLK;   // 19520
 constexpr int ADA_LD = 19584;                      // padded row length
 
 // ----------------------------------------------------------------------------- activation / dtype tags
-enum DsAct { ACT_NONE = 0, ACT_SILU = 1, ACT_TANH = 2, ACT_GELU = 3 };
+// ACT_SILU_HALF: the input is h = x/2 (the producing Linear was packed with 0.5 W, 0.5 b, exact in bf16):
+// SiLU(x) = x sigmoid(x) = h + h tanh(h) — one MUFU + one FFMA instead of two multiplies more.
+enum DsAct { ACT_NONE = 0, ACT_SILU = 1, ACT_TANH = 2, ACT_GELU = 3, ACT_SILU_HALF = 4 };
 enum DsDType { DT_F32 = 0, DT_BF16 = 1 };
 
 typedef __nv_bfloat16 bf16;
@@ -106,6 +108,11 @@ __device__ __forceinline__ float act_silu(float x) {
   if (kFast) return x * (0.5f * act_tanh<true>(0.5f * x) + 0.5f);   // x*sigmoid(x), one MUFU
   return x / (1.0f + expf(-x));
 }
+template <bool kFast>
+__device__ __forceinline__ float act_silu_half(float h) {   // SiLU(2h)
+  if (kFast) return fmaf(h, act_tanh<true>(h), h);
+  return (2.0f * h) / (1.0f + expf(-2.0f * h));
+}
 __device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 template <bool kFast>
@@ -114,6 +121,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case ACT_SILU: return act_silu<kFast>(x);
     case ACT_TANH: return act_tanh<kFast>(x);
     case ACT_GELU: return act_gelu(x);
+    case ACT_SILU_HALF: return act_silu_half<kFast>(x);
     default: return x;
   }
 }
@@ -139,6 +147,9 @@ struct Plan {
   const int* poff;       // [B+1]
   const uint32_t* node_info;   // [Mn]
   const uint32_t* pair_info;   // [Mp]
+  // [2*Mp] directed edges, source-major (d = 2*poff[mol] + r*(n-1) + c - (c > r)):
+  // x = pair row, y = atom row of the source r, z = atom row of the target c, w = molecule
+  const int4* dir_info;
 };
 __device__ __forceinline__ int pair_index(int n, int i, int j) {   // i < j < n, row-major upper triangle
   return i * n - (i * (i + 1)) / 2 + (j - i - 1);
@@ -176,3 +187,6 @@ struct DsContext;
 int gemm_simt_launch(const GemmDesc& g, bool fast_math, cudaStream_t s);
 int gemm_tc_launch(DsContext* ctx, const GemmDesc& g, cudaStream_t s);   // bf16 in, tcgen05
 int gemm_tc_init(DsContext* ctx);
+// 2-D SWIZZLE_128B tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements)
+int ds_make_tmap_2d(DsContext* ctx, CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols,
+                    int box_rows, bool f32);

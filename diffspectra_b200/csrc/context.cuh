@@ -14,7 +14,7 @@ struct DsContext {
   int spectra_version = 3;   // 0 uv, 1 ir, 2 raman, 3 allspectra
   int num_sms = 148;
   void* encode_tiled = nullptr;      // cuTensorMapEncodeTiled (driver entry point, resolved at run time)
-  int fuse_mask = 15;                // debug: bit0 LNMOD, bit1 RESGATE(node), bit2 RESGATE(edge), bit3 COORD epilogues
+  int fuse_mask = 15;                // debug: bit0 LNMOD, bit1 RESGATE(node), bit2 RESGATE(edge), bit3 COORD epilogue, bit4 fused coordinate head (coord_tc.cu; off: measured slower than k_coord_ln + COORD GEMM)
   long long launch_count = 0;        // kernels launched (or captured) through this context
   // cached CUDA graph of one sampling step (ds_sample_loop)
   cudaGraphExec_t step_graph = nullptr;

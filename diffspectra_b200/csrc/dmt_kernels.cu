@@ -382,10 +382,14 @@ __global__ void __launch_bounds__(256) k_node_ln1(Plan plan, const float* __rest
 // several CTAs are resident per SM; k / v rows and the e0|e1 pair rows are streamed through L1 with 32/64-bit
 // loads; per-target messages accumulate in registers (thread t <-> value channel t).
 constexpr int ATT_G = 8;
-__device__ __forceinline__ float2 ld_pair2(const float* p) { return *reinterpret_cast<const float2*>(p); }
-__device__ __forceinline__ float2 ld_pair2(const bf16* p) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+// 16-byte read-only load that the compiler may not sink next to its first use: a batch of these stays a batch,
+// so several rows are in flight per warp (the scheduler otherwise serialises load -> use pairs to save registers)
+__device__ __forceinline__ uint4 ldg128_pinned(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
 }
+__device__ __forceinline__ float2 ld_pair2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 template <typename AT, bool kFast, int MAXN>
 __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, const AT* __restrict__ qkv,
                                                        const AT* __restrict__ e01, const uint8_t* __restrict__ pflags,
@@ -409,29 +413,46 @@ __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, cons
   }
   __syncthreads();
   // pass 1: logits[jl][i][h] for source i -> target j
+  const unsigned rcp_n = 65536u / static_cast<unsigned>(n) + 1u;     // r / n == (r * rcp_n) >> 16 for r < 8 * 64
   for (int idx = t; idx < gsz * n * N_HEADS; idx += 256) {
     const int hh = idx & 15, r = idx >> 4;
-    const int jl = r / n, i = r - jl * n;
+    const int jl = static_cast<int>((static_cast<unsigned>(r) * rcp_n) >> 16), i = r - jl * n;
     const int row = srow[jl][i];
     if (row < 0) continue;
-    float lg;
     if (hh < N_SUB) {
       const AT* er = e01 + static_cast<size_t>(row) * E01_LD + hh * C_SUB;
       const AT* kr = qkv + static_cast<size_t>(base + i) * QKV_LD + 256 + hh * C_SUB;
       const float* qr = &sq[jl][hh * C_SUB];
       float a = 0.f;
+      if constexpr (sizeof(AT) == 2) {
+        // all 18 loads of the row pair are issued before the first use (memory-level parallelism), then
+        // k * e0 as packed bf16 multiplies (both factors are bf16 already); q and the sum stay fp32
+        __nv_bfloat162 ev[C_SUB / 2], kv[C_SUB / 2];
 #pragma unroll
-      for (int d = 0; d < C_SUB; d += 2) {
-        const float2 ev = ld_pair2(er + d);
-        const float2 kv = ld_pair2(kr + d);
-        const float2 qv = *reinterpret_cast<const float2*>(qr + d);
-        a = fmaf(qv.x * kv.x, ev.x, a);
-        a = fmaf(qv.y * kv.y, ev.y, a);
+        for (int d = 0; d < C_SUB / 2; ++d) {
+          ev[d] = *reinterpret_cast<const __nv_bfloat162*>(er + 2 * d);
+          kv[d] = *reinterpret_cast<const __nv_bfloat162*>(kr + 2 * d);
+        }
+#pragma unroll
+        for (int d = 0; d < C_SUB / 2; ++d) {
+          const float2 qv = *reinterpret_cast<const float2*>(qr + 2 * d);
+          const float2 ke = __bfloat1622float2(__hmul2(ev[d], kv[d]));
+          a = fmaf(qv.x, ke.x, a);
+          a = fmaf(qv.y, ke.y, a);
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < C_SUB; d += 2) {
+          const float2 qv = *reinterpret_cast<const float2*>(qr + d);
+          const float2 ev = ld_pair2(er + d);
+          const float2 kv = ld_pair2(kr + d);
+          a = fmaf(qv.x * kv.x, ev.x, a);
+          a = fmaf(qv.y * kv.y, ev.y, a);
+        }
       }
-      lg = a * 0.25f;                              // 1 / sqrt(out_channels = 16)
-      slog[jl][i][2 + hh] = lg;
+      slog[jl][i][2 + hh] = a * 0.25f;                 // 1 / sqrt(out_channels = 16)
     } else {
-      const int bit = hh - N_SUB;                  // 0: adj2d, 1: adjsp
+      const int bit = hh - N_SUB;                      // 0: adj2d, 1: adjsp
       slog[jl][i][bit] = ((pflags[row] >> bit) & 1) ? 1.0f : -1e10f;
     }
   }
@@ -463,17 +484,47 @@ __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, cons
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     const AT* vbase = qkv + static_cast<size_t>(base) * QKV_LD + 512 + lane * 8;
     const AT* ebase = e01 + 256 + lane * 8;
+    if constexpr (sizeof(AT) == 2) {
+      // four sources per iteration, all eight 16-byte loads issued before the first use; v * e1 as packed bf16
+      // multiplies, weighted accumulation in fp32.  Masked slots (i == j, i >= n) read a valid row with weight 0.
+      for (int i0 = 0; i0 < n; i0 += 4) {
+        uint4 vv[4], ee[4];
+        float al[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ic = min(i0 + u, n - 1);
+          const int row = srow[w][ic];
+          const bool ok = (i0 + u < n) && row >= 0;
+          al[u] = ok ? slog[w][ic][hh] : 0.f;
+          vv[u] = ldg128_pinned(vbase + static_cast<size_t>(ic) * QKV_LD);
+          ee[u] = ldg128_pinned(ebase + static_cast<size_t>(ok ? row : pbase) * E01_LD);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
+          const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&ee[u]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 pr = __bfloat1622float2(__hmul2(v2[k], e2[k]));
+            acc[2 * k] = fmaf(al[u], pr.x, acc[2 * k]);
+            acc[2 * k + 1] = fmaf(al[u], pr.y, acc[2 * k + 1]);
+          }
+        }
+      }
+    } else {
 #pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-      if (i == j) continue;
-      const float al = slog[w][i][hh];
-      const float4 v0 = load4<AT>(vbase + static_cast<size_t>(i) * QKV_LD), v1 = load4<AT>(vbase + static_cast<size_t>(i) * QKV_LD + 4);
-      const AT* er = ebase + static_cast<size_t>(srow[w][i]) * E01_LD;
-      const float4 e0 = load4<AT>(er), e1 = load4<AT>(er + 4);
-      acc[0] = fmaf(al * v0.x, e0.x, acc[0]); acc[1] = fmaf(al * v0.y, e0.y, acc[1]);
-      acc[2] = fmaf(al * v0.z, e0.z, acc[2]); acc[3] = fmaf(al * v0.w, e0.w, acc[3]);
-      acc[4] = fmaf(al * v1.x, e1.x, acc[4]); acc[5] = fmaf(al * v1.y, e1.y, acc[5]);
-      acc[6] = fmaf(al * v1.z, e1.z, acc[6]); acc[7] = fmaf(al * v1.w, e1.w, acc[7]);
+      for (int i = 0; i < n; ++i) {
+        if (i == j) continue;
+        const float al = slog[w][i][hh];
+        const AT* vr = vbase + static_cast<size_t>(i) * QKV_LD;
+        const AT* er = ebase + static_cast<size_t>(srow[w][i]) * E01_LD;
+        const float4 v0 = load4<AT>(vr), v1 = load4<AT>(vr + 4);
+        const float4 e0 = load4<AT>(er), e1 = load4<AT>(er + 4);
+        acc[0] = fmaf(al * v0.x, e0.x, acc[0]); acc[1] = fmaf(al * v0.y, e0.y, acc[1]);
+        acc[2] = fmaf(al * v0.z, e0.z, acc[2]); acc[3] = fmaf(al * v0.w, e0.w, acc[3]);
+        acc[4] = fmaf(al * v1.x, e1.x, acc[4]); acc[5] = fmaf(al * v1.y, e1.y, acc[5]);
+        acc[6] = fmaf(al * v1.z, e1.z, acc[6]); acc[7] = fmaf(al * v1.w, e1.w, acc[7]);
+      }
     }
     float* ho = hn + static_cast<size_t>(base + j) * 256 + lane * 8;
     *reinterpret_cast<float4*>(ho) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -898,6 +949,10 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       // equivariant coordinate update
       DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, s));
       DS_TRY(linear(ctx, w.hb, 256, bw.wab, 256, bw.bab, nullptr, 0, w.ab, 512, AD, Mn, 512, 256, ACT_NONE, s));
+      if (kFast && (ctx->fuse_mask & 16)) {
+        // whole coordinate head in one kernel: the LN+modulate operand never leaves the SM
+        DS_TRY(coord_fused_launch(ctx, plan, w.ab, w.gp, ada_l, w.pflags, bw.wc1, bw.bc1, bw.wc2, w.wdir, s));
+      } else {
       k_coord_ln<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.ab), reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
                                                         reinterpret_cast<AT*>(w.Z), dflags);
       LAUNCH_CHECK(ctx);
@@ -907,9 +962,10 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         g.a_dtype = DT_BF16; g.mode = GEMM_COORD; g.wc2 = bw.wc2; g.pflags = dflags; g.wdir = w.wdir;
         DS_TRY(gemm_tc_launch(ctx, g, s));
       } else {
-        DS_TRY(linear(ctx, w.Z, 256, bw.wc1, 256, bw.bc1, nullptr, 0, w.u1, 256, AD, Md, 256, 256, ACT_SILU, s));
+        DS_TRY(linear(ctx, w.Z, 256, bw.wc1, 256, bw.bc1, nullptr, 0, w.u1, 256, AD, Md, 256, 256, kFast ? ACT_SILU_HALF : ACT_SILU, s));
         k_coord_out<AT, kFast><<<cdiv(Md, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.u1), bw.wc2, dflags, w.wdir);
         LAUNCH_CHECK(ctx);
+      }
       }
     }
     k_pos_update<<<B, 64, 0, s>>>(plan, w.wdir, bw.coord_scale, w.pos);

@@ -14,7 +14,7 @@
 //   STORE    act(acc + bias + addmat)                                  every nn.Linear (+SiLU/tanh/GELU)
 //   LNMOD    modulate(LayerNorm(acc + bias), shift[mol], scale[mol])    dmt.py:139,149 (edge_emb -> norm1_edge)
 //   RESGATE  resid + gate[mol] * (acc + bias) -> fp32 stream + bf16 copy  dmt.py:162-163,168-169 (FFN residuals)
-//   COORD    mean(tanh(W2 . SiLU(acc + bias)) * [1, adj2d, adjsp])       dmt.py:32-35,45-51 (coord_mlp + heads)
+//   COORD    mean(tanh(W2 . SiLU(2 (acc + bias))) * [1, adj2d, adjsp])   dmt.py:32-35,45-51 (coord_mlp + heads; W, bias pre-halved)
 //   EHEAD    [w_e . SiLU(acc[:32] + b), w_t . SiLU(acc[32:] + b)]          dmt.py:234-247,394 (edge heads, layers 2+4)
 #include "context.cuh"
 #include "ptx_sm100.cuh"
@@ -156,8 +156,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ CUtensorMap tmF, Epi ep, int M, int N, int K) {
   using C = Cfg<BN, MODE, TMA_OUT>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment is requested from the compiler/driver (no static shared memory in this kernel), so plain
+  // pointer arithmetic keeps the shared address space visible and the epilogues compile to LDS/STS, not generic LD/ST.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
   uint8_t* smA = smem;
   uint8_t* smW = smem + C::kStages * C::kABytes;
   uint8_t* staging = smem + C::kStages * C::kStageBytes;                 // 1024-aligned (stage sizes are multiples of 1 KB)
@@ -179,6 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = m_tiles * n_tiles;
 
   if (warp == 8 && lane == 0) {
+    if (ptx::smem_u32(smem) & 1023u) __trap();      // SWIZZLE_128B tiles need a 1024-byte aligned base
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
     if (TMA_OUT) ptx::prefetch_tmap(&tmO);
@@ -422,7 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float4 w = swc2[c + i];
-            const float v = act_silu<true>(f[i] + w.w);
+            const float v = act_silu_half<true>(f[i] + w.w);      // coord_mlp.0 is packed with 0.5 W, 0.5 b
             s0 = fmaf(v, w.x, s0);
             s1 = fmaf(v, w.y, s1);
             s2 = fmaf(v, w.z, s2);
@@ -503,6 +506,11 @@ int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
 }
 
 }  // namespace
+
+int ds_make_tmap_2d(DsContext* ctx, CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_cols,
+                    int box_rows, bool f32) {
+  return make_tmap(ctx, map, base, rows, cols, ld, box_cols, box_rows, f32);
+}
 
 int gemm_tc_init(DsContext* ctx) {
   void* fn = nullptr;

@@ -144,6 +144,11 @@ int denoise_packed(DsContext* ctx, const PackedWeights& pw, const Plan& plan, co
                    const float* cond_x, const float* cond_e, const float* noise_level, StepRef sr,
                    const float* ctx_emb, float* pred_x, float* pred_e, DenoiseWs& w, cudaStream_t s);
 
+// fused coordinate head of one block (coord_tc.cu): LN+modulate operand built in shared memory -> tcgen05 -> w[d]
+int coord_fused_launch(DsContext* ctx, const Plan& plan, const void* ab, const void* gp, const float* ada_l,
+                       const uint8_t* pflags, const void* wc1, const float* bc1, const float* wc2, float* wdir,
+                       cudaStream_t s);
+
 int launch_pack_dense(DsContext* ctx, const Plan& plan, const float* x, const float* ex, float* xs, float* es,
                       cudaStream_t s);
 int launch_unpack_dense(DsContext* ctx, const Plan& plan, const float* xs, const float* es, float* x, float* ex,

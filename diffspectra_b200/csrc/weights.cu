@@ -8,11 +8,12 @@
 namespace {
 
 template <typename TD>
-__global__ void k_copy2d(const float* __restrict__ src, int src_ld, TD* __restrict__ dst, int dst_ld, int rows, int cols) {
+__global__ void k_copy2d(const float* __restrict__ src, int src_ld, TD* __restrict__ dst, int dst_ld, int rows, int cols,
+                         float scale) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
   const int r = idx / cols, c = idx % cols;
-  dst[static_cast<size_t>(r) * dst_ld + c] = from_f32<TD>(src[static_cast<size_t>(r) * src_ld + c]);
+  dst[static_cast<size_t>(r) * dst_ld + c] = from_f32<TD>(scale * src[static_cast<size_t>(r) * src_ld + c]);
 }
 // dst[c, r] = src[r, c]
 __global__ void k_transpose(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
@@ -46,23 +47,24 @@ struct Packer {
   float* alloc_f32(size_t elems) { return static_cast<float*>(arena.take(elems * 4)); }
 
   // copy a [rows, cols] sub-block (src pre-offset, leading dim src_ld) into dst (+ element offset), dtype act or f32
-  void copy(const float* src, int src_ld, void* dst, size_t dst_off, int dst_ld, int rows, int cols, bool act) {
+  void copy(const float* src, int src_ld, void* dst, size_t dst_off, int dst_ld, int rows, int cols, bool act,
+            float scale = 1.0f) {
     if (arena.dry || err != DS_OK || src == nullptr || dst == nullptr) return;
     const int n = rows * cols;
     if (act && bf)
-      k_copy2d<bf16><<<(n + 255) / 256, 256, 0, s>>>(src, src_ld, static_cast<bf16*>(dst) + dst_off, dst_ld, rows, cols);
+      k_copy2d<bf16><<<(n + 255) / 256, 256, 0, s>>>(src, src_ld, static_cast<bf16*>(dst) + dst_off, dst_ld, rows, cols, scale);
     else
-      k_copy2d<float><<<(n + 255) / 256, 256, 0, s>>>(src, src_ld, static_cast<float*>(dst) + dst_off, dst_ld, rows, cols);
+      k_copy2d<float><<<(n + 255) / 256, 256, 0, s>>>(src, src_ld, static_cast<float*>(dst) + dst_off, dst_ld, rows, cols, scale);
   }
   // whole matrix [rows, cols] in the act dtype
-  const void* mat(const std::string& name, int rows, int cols) {
+  const void* mat(const std::string& name, int rows, int cols, float scale = 1.0f) {
     void* d = alloc_act(static_cast<size_t>(rows) * cols);
-    copy(get(name), cols, d, 0, cols, rows, cols, true);
+    copy(get(name), cols, d, 0, cols, rows, cols, true, scale);
     return d;
   }
-  const float* vec(const std::string& name, int n) {
+  const float* vec(const std::string& name, int n, float scale = 1.0f) {
     float* d = alloc_f32(n);
-    copy(get(name), n, d, 0, n, 1, n, false);
+    copy(get(name), n, d, 0, n, 1, n, false, scale);
     return d;
   }
 };
@@ -148,8 +150,9 @@ int build(Packer& P, PackedWeights& pw) {
     P.copy(P.get(p + "equi_update.input_lin.bias"), 256, bab, 0, 256, 1, 256, false);
     b.wab = wab;
     b.bab = bab;
-    b.wc1 = P.mat(p + "equi_update.coord_mlp.0.weight", 256, 256);
-    b.bc1 = P.vec(p + "equi_update.coord_mlp.0.bias", 256);
+    // bf16 mode: coord_mlp.0 is stored halved (exact in bf16) so that its SiLU is h + h tanh(h) (ACT_SILU_HALF)
+    b.wc1 = P.mat(p + "equi_update.coord_mlp.0.weight", 256, 256, P.bf ? 0.5f : 1.0f);
+    b.bc1 = P.vec(p + "equi_update.coord_mlp.0.bias", 256, P.bf ? 0.5f : 1.0f);
     b.wc2 = P.vec(p + "equi_update.coord_mlp.2.weight", 3 * 256);
     b.coord_scale = P.vec(p + "equi_update.coord_norm.scale", 1);
     b.rbf_means = P.vec(p + "dist_layer.means.weight", 63);

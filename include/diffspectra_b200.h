@@ -122,8 +122,8 @@ int ds_gemm(ds_ctx* ctx, int use_tensor_cores, const void* A, int lda, const voi
 
 /* Test hook for the fused epilogues of the tcgen05 GEMM (bf16 A/W).  mode 1 = LNMOD: out(bf16)[M,64] =
  * modulate(LayerNorm(A W^T + bias), ada[mol][off_a:], ada[mol][off_b:]);  mode 2 = RESGATE: out(f32) = resid +
- * ada[mol][off_a:] * (A W^T + bias), out2(bf16) = copy;  mode 3 = COORD: wdir[row] = mean(tanh(wc2 . SiLU(A W^T +
- * bias)) * [1, dflags bit0, dflags bit1]).  mol = row_info[row] >> info_shift; ada rows have stride 19584 floats. */
+ * ada[mol][off_a:] * (A W^T + bias), out2(bf16) = copy;  mode 3 = COORD: wdir[row] = mean(tanh(wc2 . SiLU(2 (A W^T +
+ * bias))) * [1, dflags bit0, dflags bit1]) (W, bias = the halved first layer).  mol = row_info[row] >> info_shift; ada rows have stride 19584 floats. */
 int ds_gemm_fused(ds_ctx* ctx, int mode, const void* A, int lda, const void* W, int ldw, const float* bias, int M, int N,
                   int K, const unsigned* row_info, int info_shift, const float* ada, int off_a, int off_b,
                   const float* resid, int ldres, void* out, int ldo, void* out2, int ldo2, const float* wc2,

@@ -28,9 +28,18 @@ def keyed_state_dict(module, salt=0, coord_scale=None):
     return sd
 
 
-def build_model(version, salt=0, coord_scale=None, precision='fp32', device='cuda'):
+def build_model(version, salt=0, coord_scale=None, precision='fp32', device='cuda', min_rbf_std=None):
+    """min_rbf_std: clamp |stds| of every Gaussian RBF layer from below.  The reference initialises them U(0,3)
+    (models/layers.py:325-326); a std of ~0.003 makes that channel a spike of height ~130 that flips on/off with a
+    1e-3 change of the distance, so tests that are NOT about those ill-conditioned channels (batch invariance, the
+    N=64 shape) use well-conditioned Gaussians."""
     from diffspectra_b200.config import get_config
     from diffspectra_b200.model import DMT_B200
     m = DMT_B200(get_config(version, device=device, precision=precision)).eval()
-    keyed_state_dict(m, salt, coord_scale)
+    sd = keyed_state_dict(m, salt, coord_scale)
+    if min_rbf_std is not None:
+        for k, v in sd.items():
+            if k.endswith('stds.weight'):
+                v.clamp_(min=min_rbf_std)
+        m.load_state_dict(sd)
     return m.to(device)

@@ -148,7 +148,8 @@ def test_gemm_fused_coord(ctx, M):
     wc2 = torch.randn(3, 256, device='cuda', generator=g) / 16
     dflags = torch.randint(0, 4, (M,), device='cuda', generator=g, dtype=torch.uint8)
     wdir = torch.full((M + 4,), -7.0, device='cuda')
-    L.check(L.lib().ds_gemm_fused(ctx, 3, L.ptr(A), K, L.ptr(W), K, L.ptr(bias), M, N, K, None, 0, None, 0, 0, None, 0, None, 0,
+    Wh, bh = (W.float() * 0.5).bfloat16(), bias * 0.5          # COORD takes the first layer pre-halved: SiLU(2 (A Wh^T + bh))
+    L.check(L.lib().ds_gemm_fused(ctx, 3, L.ptr(A), K, L.ptr(Wh), K, L.ptr(bh), M, N, K, None, 0, None, 0, 0, None, 0, None, 0,
                                   None, 0, L.ptr(wc2), L.ptr(dflags), L.ptr(wdir), L.stream_ptr()), 'ds_gemm_fused')
     torch.cuda.synchronize()
     u = torch.tanh(torch.nn.functional.silu(A.float() @ W.float().t() + bias) @ wc2.t())

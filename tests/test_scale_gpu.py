@@ -34,7 +34,7 @@ def _inputs(n, N, seed, dev='cuda'):
 @pytest.mark.parametrize('precision,tol', [('fp32', 2e-6), ('bf16', 2e-2)])
 def test_batch_1024_matches_small_batches(precision, tol):
     version = 'allspectra'
-    model = build_model(version, salt=5, coord_scale=0.02, precision=precision)
+    model = build_model(version, salt=5, coord_scale=0.02, precision=precision, min_rbf_std=0.3)
     n = W.sample_n_atoms(1024, seed=1234)
     n[0] = 29
     N = 29
@@ -59,7 +59,7 @@ def test_batch_1024_matches_small_batches(precision, tol):
 def test_stress_shape_n64_matches_oracle(precision, tol):
     """BASELINE configs[4]: padded molecules with up to 64 atoms."""
     version = 'allspectra'
-    model = build_model(version, salt=6, coord_scale=0.01, precision=precision)
+    model = build_model(version, salt=6, coord_scale=0.01, precision=precision, min_rbf_std=0.3)
     sd = {k: (v.double() if v.is_floating_point() else v) for k, v in model.state_dict().items()}
     n = torch.tensor([64, 40, 33, 64, 1])
     nm, em, x, ex, cx, cex, nl = _inputs(n, 64, seed=31)
@@ -93,3 +93,20 @@ def test_philox_loop_is_sharding_invariant():
                                    gid_base=1000 + lo)
             # same noise, same maths per molecule; tiles are cut differently, so allow fp32 summation-order noise only
             assert rel_l2(part[0], full[0][lo:hi]) < 1e-4 and rel_l2(part[1], full[1][lo:hi]) < 1e-4
+
+
+def test_fused_coordinate_head_matches_split_path(monkeypatch):
+    """coord_tc.cu (operand built in shared memory -> tcgen05 -> w) is an opt-in alternative to k_coord_ln + the COORD
+    GEMM (DS_FUSE_MASK bit 4): both must give the same denoiser output up to bf16 operand rounding order."""
+    version = 'ir'
+    n = W.sample_n_atoms(64, seed=3)
+    nm, em, x, ex, cx, cex, nl = _inputs(n, 29, seed=41)
+    ctx = W.synthetic_spectra(64, version, seed=6).cuda()
+    outs = []
+    for mask in ('15', '31'):
+        monkeypatch.setenv('DS_FUSE_MASK', mask)            # read by ds_create
+        model = build_model(version, salt=4, coord_scale=0.02, precision='bf16', min_rbf_std=0.3)
+        with torch.no_grad():
+            outs.append(model(nl, x, nm, em, context=ctx, edge_x=ex, noise_level=nl, cond_x=cx, cond_edge_x=cex))
+    assert rel_l2(outs[1][0][..., :3], outs[0][0][..., :3]) < 1e-5
+    assert rel_l2(outs[1][0][..., 3:], outs[0][0][..., 3:]) < 1e-5 and rel_l2(outs[1][1], outs[0][1]) < 1e-5
