@@ -17,6 +17,8 @@ void ds_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool g_ds_use_pdl = false;     // measured on B200: no gain with the implicit trigger (graph replay gaps are already ~0), -3.5% with an early trigger
+
 extern "C" {
 
 const char* ds_last_error(void) { return g_err; }
@@ -43,6 +45,7 @@ int ds_create(ds_ctx** out, int device, int mode, int spectra_version) {
   c->spectra_version = spectra_version;
   c->num_sms = prop.multiProcessorCount;
   if (const char* fm = getenv("DS_FUSE_MASK")) c->fuse_mask = atoi(fm);
+  if (const char* pd = getenv("DS_PDL")) g_ds_use_pdl = atoi(pd) != 0;
   int r = gemm_tc_init(c);
   if (r != DS_OK) {
     ds_ctx_free(c);

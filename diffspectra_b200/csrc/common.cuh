@@ -43,6 +43,33 @@
 
 void ds_set_error(const char* fmt, ...);
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the step graph CAN be launched with programmaticStreamSerialization: it may become resident while
+// its predecessor drains, runs its prologue, and blocks in pdl_wait() until the predecessor has completed and its
+// memory is visible.  pdl_trigger() at the top lets the successor do the same.  (A kernel launched without the
+// attribute, or first in the stream, sees both as no-ops.)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef DS_PDL_EARLY_TRIGGER
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_trigger() {}     // implicit trigger at grid completion: only the launch is pre-staged
+#endif
+extern bool g_ds_use_pdl;      // DS_PDL=1 enables the launch attribute (off by default, see api_core.cu)
+template <typename... KArgs, typename... Args>
+inline cudaError_t ds_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_ds_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------- model dimensions (QM9S config)
 // configs/diffspectra_qm9s.py:53-76 — the kernels are specialised for these.
 constexpr int D_NODE = 256;    // model.nf

@@ -71,6 +71,7 @@ __device__ __forceinline__ void store_z_row(uint8_t* ztile, int lr, int lane, co
 
 __global__ void __launch_bounds__(kThreads, 1)
 coord_fused_kernel(const __grid_constant__ CUtensorMap tmW, CoordArgs a) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smZ = smem;                              // [2][64 KB]
   uint8_t* smW = smem + 2 * kZBytes;                // [2][32 KB]
@@ -108,6 +109,7 @@ coord_fused_kernel(const __grid_constant__ CUtensorMap tmW, CoordArgs a) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 8) {
     // ===================== coord_mlp.0 k-blocks: L2 -> shared =====================
@@ -289,7 +291,7 @@ int coord_fused_launch(DsContext* ctx, const Plan& plan, const void* ab, const v
   a.Md = Md;
   const int tiles = (Md + TM - 1) / TM;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  coord_fused_kernel<<<grid, kThreads, kSmem, s>>>(tmW, a);
+  ds_launch(coord_fused_kernel, dim3(grid), dim3(kThreads), kSmem, s, tmW, a);
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;
   return DS_OK;

@@ -48,6 +48,8 @@ template <typename AT>
 __global__ void __launch_bounds__(256) k_time_feat(const float* __restrict__ nl, StepRef sr, const float* __restrict__ freq,
                                                    const float* __restrict__ w1, const float* __restrict__ b1,
                                                    AT* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float f[17];
   const int b = blockIdx.x;
   const float x = nl ? nl[b] : sr.coef[(*sr.step) * 4 + 3];
@@ -77,6 +79,8 @@ __global__ void __launch_bounds__(256) k_root_nodes(int Mn, const float* __restr
                                                     const float* __restrict__ w, const float* __restrict__ b,
                                                     float* __restrict__ h, AT* __restrict__ hb, AT* __restrict__ ahid,
                                                     float* __restrict__ pos) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float in[12];
   const int m = blockIdx.x;
   const int t = threadIdx.x;
@@ -96,6 +100,8 @@ __global__ void __launch_bounds__(256) k_root_nodes(int Mn, const float* __restr
 // batch-global "all conditioning distances are zero" predicate (dmt.py:364)
 __global__ void k_root_pair_flags(Plan plan, const float* __restrict__ cond, const float* __restrict__ cond_e,
                                   uint8_t* __restrict__ pflags, int* __restrict__ flags) {
+  pdl_trigger();
+  pdl_wait();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   bool nz = false;
   if (p < plan.Mp) {
@@ -126,6 +132,8 @@ __global__ void __launch_bounds__(256) k_root_pairs(Plan plan, const float* __re
                                                     const float* __restrict__ stds, const float* __restrict__ w,
                                                     const float* __restrict__ b, float* __restrict__ e,
                                                     AT* __restrict__ X, AT* __restrict__ ehid) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float in[32][69];
   __shared__ float wt[68][64];     // transposed edge_emb weight
   for (int idx = threadIdx.x; idx < 64 * 68; idx += 256) wt[idx % 68][idx / 68] = w[idx];
@@ -175,6 +183,8 @@ __global__ void __launch_bounds__(256) k_root_operand(Plan plan, const float* __
                                                       const float* __restrict__ cond_e, const float* __restrict__ ada,
                                                       const int* __restrict__ flags, const float* __restrict__ means,
                                                       const float* __restrict__ stds, AT* __restrict__ xr) {
+  pdl_trigger();
+  pdl_wait();
   const int p = blockIdx.x * 32 + (threadIdx.x >> 3), k0 = (threadIdx.x & 7) * 8;
   if (p >= plan.Mp) return;
   int mol, i, j;
@@ -206,6 +216,8 @@ __global__ void __launch_bounds__(256) k_root_operand(Plan plan, const float* __
 // dst[:, 0:64] (ld dst_ld) = src[:, 0:64] (ld src_ld), 16 bytes per thread
 template <typename AT>
 __global__ void k_copy64(int rows, const AT* __restrict__ src, int src_ld, AT* __restrict__ dst, int dst_ld) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int per = 16 / sizeof(AT);
   constexpr int chunks = 64 / per;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -222,6 +234,8 @@ template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict__ pos, const float* __restrict__ ada, int l,
                                              const float* __restrict__ means, const float* __restrict__ stds,
                                              AT* __restrict__ X) {
+  pdl_trigger();
+  pdl_wait();
   const int k0 = (threadIdx.x & 7) * 8;
   float mean[8], sd[8], coef[8];     // fast mode: sd / coef hold the RECIPROCALS (2 multiplies instead of 2 divisions)
 #pragma unroll
@@ -311,6 +325,8 @@ __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_pair_ln1(Plan plan, const float* __restrict__ y1, const float* __restrict__ ada, int l,
                                                   AT* __restrict__ ea) {
+  pdl_trigger();
+  pdl_wait();
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (p >= plan.Mp) return;
   const int mol = plan.pair_info[p] >> 12;
@@ -367,6 +383,8 @@ __device__ __forceinline__ void store8(T* row, int lane, const float (&v)[8]) {
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_node_ln1(Plan plan, const float* __restrict__ h, const float* __restrict__ ada, int l,
                                                   AT* __restrict__ hh) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= plan.Mn) return;
   const int mol = plan.node_info[m] >> 6;
@@ -394,6 +412,8 @@ template <typename AT, bool kFast, int MAXN>
 __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, const AT* __restrict__ qkv,
                                                        const AT* __restrict__ e01, const uint8_t* __restrict__ pflags,
                                                        float* __restrict__ hn, AT* __restrict__ hnb) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float sq[ATT_G][256];
   __shared__ float slog[ATT_G][MAXN][N_HEADS];
   __shared__ int srow[ATT_G][MAXN];
@@ -540,6 +560,8 @@ template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_node_update1(Plan plan, const float* __restrict__ h, const float* __restrict__ hn,
                                                       const float* __restrict__ ada, int l, float* __restrict__ h1,
                                                       AT* __restrict__ h1b) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= plan.Mn) return;
   const int mol = plan.node_info[m] >> 6;
@@ -560,6 +582,8 @@ template <typename AT>
 __global__ void __launch_bounds__(256) k_node_update2(Plan plan, const float* __restrict__ h1, const float* __restrict__ f2,
                                                       const float* __restrict__ ada, int l, float* __restrict__ h,
                                                       AT* __restrict__ hb) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= plan.Mn) return;
   const int mol = plan.node_info[m] >> 6;
@@ -580,6 +604,8 @@ template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_edge_update1(Plan plan, const float* __restrict__ e, const float* __restrict__ pn,
                                                       const float* __restrict__ n2e_b, const float* __restrict__ ada, int l,
                                                       float* __restrict__ e1f, AT* __restrict__ e1b) {
+  pdl_trigger();
+  pdl_wait();
   const int p = blockIdx.x * 16 + (threadIdx.x >> 4), c0 = (threadIdx.x & 15) * 4;
   const bool ok = p < plan.Mp;
   const int pp = ok ? p : plan.Mp - 1;
@@ -616,6 +642,8 @@ template <typename AT>
 __global__ void __launch_bounds__(256) k_edge_update2(Plan plan, const float* __restrict__ e1f, const float* __restrict__ f4,
                                                       const float* __restrict__ ada, int l, float* __restrict__ e,
                                                       AT* __restrict__ X) {
+  pdl_trigger();
+  pdl_wait();
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (p >= plan.Mp) return;
   const int mol = plan.pair_info[p] >> 12;
@@ -636,6 +664,8 @@ template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const AT* __restrict__ ab, const AT* __restrict__ gp,
                                                   const float* __restrict__ ada, int l, const uint8_t* __restrict__ pflags,
                                                   AT* __restrict__ Z, uint8_t* __restrict__ dflags) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= plan.Mn) return;
   const uint32_t info = plan.node_info[m];
@@ -695,6 +725,8 @@ __global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const AT* __restric
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_coord_out(Plan plan, const AT* __restrict__ u1, const float* __restrict__ wc2,
                                                    const uint8_t* __restrict__ dflags, float* __restrict__ wdir) {
+  pdl_trigger();
+  pdl_wait();
   const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (d >= 2 * plan.Mp) return;
   float v[8];
@@ -720,6 +752,8 @@ __global__ void __launch_bounds__(256) k_coord_out(Plan plan, const AT* __restri
 // (dmt.py:40-41,53-58, layers.py:344-347, dmt.py:385-386)
 __global__ void __launch_bounds__(64) k_pos_update(Plan plan, const float* __restrict__ wdir, const float* __restrict__ scale_p,
                                                    float* __restrict__ pos) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sp[MAX_ATOMS][3];
   __shared__ float red[3][2];
   const int mol = blockIdx.x, r = threadIdx.x;
@@ -762,6 +796,8 @@ __global__ void __launch_bounds__(64) k_pos_update(Plan plan, const float* __res
 template <typename AT>
 __global__ void __launch_bounds__(256) k_node_head_out(Plan plan, const AT* __restrict__ n2, const float* __restrict__ w,
                                                        const float* __restrict__ b, float* __restrict__ pred) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= plan.Mn) return;
   const float4 v = load4<AT>(n2 + static_cast<size_t>(m) * 128 + 4 * lane);
@@ -778,6 +814,8 @@ template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_edge_head_out(Plan plan, const AT* __restrict__ eh1, const float* __restrict__ w2t,
                                                        const float* __restrict__ b2, const float* __restrict__ w4,
                                                        const float* __restrict__ b4, float* __restrict__ pred_e) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float row[8][128];
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.x * 8 + wi;
@@ -798,12 +836,16 @@ __global__ void __launch_bounds__(256) k_edge_head_out(Plan plan, const AT* __re
 
 // NaN guard (dmt.py:407-409) is batch-global: first detect, then zero / re-centre (dmt.py:402-412)
 __global__ void k_pos_nan_flag(int Mn, const float* __restrict__ pos, int* __restrict__ flags) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool bad = (i < Mn * 3) && isnan(pos[i]);
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&flags[1], 1);
 }
 __global__ void __launch_bounds__(64) k_pos_final(Plan plan, const float* __restrict__ pos, const int* __restrict__ flags,
                                                   float* __restrict__ pred) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[3][2];
   const int mol = blockIdx.x, r = threadIdx.x;
   const int n = plan.n_atoms[mol], base = plan.noff[mol];
@@ -824,6 +866,8 @@ __global__ void __launch_bounds__(64) k_pos_final(Plan plan, const float* __rest
 }
 
 __global__ void k_zero_flags(int* flags) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x < 4) flags[threadIdx.x] = 0;
 }
 
@@ -843,35 +887,35 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
   const int AD = kFast ? DT_BF16 : DT_F32;
   AT* X = reinterpret_cast<AT*>(w.X);
 
-  k_zero_flags<<<1, 32, 0, s>>>(w.flags);
+  ds_launch(k_zero_flags, dim3(1), dim3(32), 0, s, w.flags);
   LAUNCH_CHECK(ctx);
   // time embedding (+ cached spectral context) -> SiLU -> per-molecule adaLN table
-  k_time_feat<AT><<<B, 256, 0, s>>>(noise_level, sr, pw.tm_freq, pw.tm1_w, pw.tm1_b, reinterpret_cast<AT*>(w.tfeat));
+  ds_launch(k_time_feat<AT>, dim3(B), dim3(256), 0, s, noise_level, sr, pw.tm_freq, pw.tm1_w, pw.tm1_b, reinterpret_cast<AT*>(w.tfeat));
   LAUNCH_CHECK(ctx);
   DS_TRY(linear(ctx, w.tfeat, D_TIME, pw.tm3_w, D_TIME, pw.tm3_b, ctx_emb, D_TIME, w.s_act, D_TIME, AD, B, D_TIME, D_TIME,
                 ACT_SILU, s));
   DS_TRY(linear(ctx, w.s_act, D_TIME, pw.w_ada, D_TIME, pw.b_ada, nullptr, 0, w.ada, ADA_LD, DT_F32, B, ADA_LD, D_TIME,
                 ACT_NONE, s));
   // root embeddings
-  k_root_nodes<AT><<<Mn, 256, 0, s>>>(Mn, xs, cond_x, pw.node_emb_w, pw.node_emb_b, w.h, reinterpret_cast<AT*>(w.hb),
+  ds_launch(k_root_nodes<AT>, dim3(Mn), dim3(256), 0, s, Mn, xs, cond_x, pw.node_emb_w, pw.node_emb_b, w.h, reinterpret_cast<AT*>(w.hb),
                                       reinterpret_cast<AT*>(w.ahid), w.pos);
   LAUNCH_CHECK(ctx);
   if (Mp > 0) {
-    k_root_pair_flags<<<cdiv(Mp, 256), 256, 0, s>>>(plan, cond_x, cond_e, w.pflags, w.flags);
+    ds_launch(k_root_pair_flags, dim3(cdiv(Mp, 256)), dim3(256), 0, s, plan, cond_x, cond_e, w.pflags, w.flags);
     LAUNCH_CHECK(ctx);
     if (kFast) {
       AT* xr = reinterpret_cast<AT*>(w.xr);
-      k_root_operand<AT, kFast><<<cdiv(Mp, 32), 256, 0, s>>>(plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means, pw.root_stds, xr);
+      ds_launch(k_root_operand<AT, kFast>, dim3(cdiv(Mp, 32)), dim3(256), 0, s, plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means, pw.root_stds, xr);
       LAUNCH_CHECK(ctx);
       GemmDesc g;    // e = edge_emb(operand): fp32 stream + bf16 copy into the [dist | e] operand
       g.A = xr; g.lda = 128; g.W = pw.root_w; g.ldw = 128; g.bias = pw.edge_emb_b; g.out = w.e; g.ldo = 64;
       g.M = Mp; g.N = 64; g.K = 128; g.a_dtype = DT_BF16; g.out_dtype = DT_F32; g.mode = GEMM_RESGATE;
       g.out2 = X + 64; g.ldo2 = 128;
       DS_TRY(gemm_tc_launch(ctx, g, s));
-      k_copy64<AT><<<cdiv(Mp * 8, 256), 256, 0, s>>>(Mp, X + 64, 128, reinterpret_cast<AT*>(w.ehid), 192);
+      ds_launch(k_copy64<AT>, dim3(cdiv(Mp * 8, 256)), dim3(256), 0, s, Mp, X + 64, 128, reinterpret_cast<AT*>(w.ehid), 192);
       LAUNCH_CHECK(ctx);
     } else {
-      k_root_pairs<AT, kFast><<<cdiv(Mp, 32), 256, 0, s>>>(plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means,
+      ds_launch(k_root_pairs<AT, kFast>, dim3(cdiv(Mp, 32)), dim3(256), 0, s, plan, es, cond_x, cond_e, w.ada, w.flags, pw.root_means,
                                                           pw.root_stds, pw.edge_emb_w, pw.edge_emb_b, w.e, X,
                                                           reinterpret_cast<AT*>(w.ehid));
       LAUNCH_CHECK(ctx);
@@ -885,7 +929,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     const BlockWeights& bw = pw.blk[l];
     const float* ada_l = w.ada + l * ADA_BLK;
     if (Mp > 0) {
-      k_rbf<AT, kFast><<<cdiv(Mp, 128), 256, 0, s>>>(plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
+      ds_launch(k_rbf<AT, kFast>, dim3(cdiv(Mp, 128)), dim3(256), 0, s, plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
       LAUNCH_CHECK(ctx);
       if (kFast && (ctx->fuse_mask & 1)) {
         // edge_emb -> LayerNorm -> modulate fused in the GEMM epilogue
@@ -896,24 +940,24 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         DS_TRY(gemm_tc_launch(ctx, g, s));
       } else {
         DS_TRY(linear(ctx, X, 128, bw.edge_emb_w, 128, bw.edge_emb_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
-        k_pair_ln1<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.y1, w.ada, l, reinterpret_cast<AT*>(w.ea));
+        ds_launch(k_pair_ln1<AT, kFast>, dim3(cdiv(Mp, 8)), dim3(256), 0, s, plan, w.y1, w.ada, l, reinterpret_cast<AT*>(w.ea));
         LAUNCH_CHECK(ctx);
       }
       DS_TRY(linear(ctx, w.ea, 64, bw.w01, 64, nullptr, nullptr, 0, w.e01, E01_LD, AD, Mp, E01_LD, 64, ACT_TANH, s));
     }
-    k_node_ln1<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h, w.ada, l, reinterpret_cast<AT*>(w.hh));
+    ds_launch(k_node_ln1<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, w.h, w.ada, l, reinterpret_cast<AT*>(w.hh));
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hh, 256, bw.wqkv, 256, bw.bqkv, nullptr, 0, w.qkv, QKV_LD, AD, Mn, QKV_LD, 256, ACT_NONE, s));
     if (plan.N <= 32)
-      k_attention_grp<AT, kFast, 32><<<B * ngrp, 256, 0, s>>>(plan, ngrp, reinterpret_cast<const AT*>(w.qkv), reinterpret_cast<const AT*>(w.e01), w.pflags,
+      ds_launch(k_attention_grp<AT, kFast, 32>, dim3(B * ngrp), dim3(256), 0, s, plan, ngrp, reinterpret_cast<const AT*>(w.qkv), reinterpret_cast<const AT*>(w.e01), w.pflags,
                                                               w.hn, reinterpret_cast<AT*>(w.hnb));
     else
-      k_attention_grp<AT, kFast, 64><<<B * ngrp, 256, 0, s>>>(plan, ngrp, reinterpret_cast<const AT*>(w.qkv), reinterpret_cast<const AT*>(w.e01), w.pflags,
+      ds_launch(k_attention_grp<AT, kFast, 64>, dim3(B * ngrp), dim3(256), 0, s, plan, ngrp, reinterpret_cast<const AT*>(w.qkv), reinterpret_cast<const AT*>(w.e01), w.pflags,
                                                               w.hn, reinterpret_cast<AT*>(w.hnb));
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hnb, 256, bw.n2e_w, 256, nullptr, nullptr, 0, w.pn, 64, DT_F32, Mn, 64, 256, ACT_NONE, s));
     // node stream
-    k_node_update1<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h, w.hn, w.ada, l, w.h1, reinterpret_cast<AT*>(w.h1b));
+    ds_launch(k_node_update1<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, w.h, w.hn, w.ada, l, w.h1, reinterpret_cast<AT*>(w.h1b));
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.h1b, 256, bw.ff1_w, 256, bw.ff1_b, nullptr, 0, w.f1, 512, AD, Mn, 512, 256, ACT_SILU, s));
     if (kFast && (ctx->fuse_mask & 2)) {
@@ -925,12 +969,12 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       DS_TRY(gemm_tc_launch(ctx, g, s));
     } else {
       DS_TRY(linear(ctx, w.f1, 512, bw.ff2_w, 512, bw.ff2_b, nullptr, 0, w.f2, 256, DT_F32, Mn, 256, 512, ACT_NONE, s));
-      k_node_update2<AT><<<cdiv(Mn, 8), 256, 0, s>>>(plan, w.h1, w.f2, w.ada, l, w.h, reinterpret_cast<AT*>(w.hb));
+      ds_launch(k_node_update2<AT>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, w.h1, w.f2, w.ada, l, w.h, reinterpret_cast<AT*>(w.hb));
       LAUNCH_CHECK(ctx);
     }
     if (Mp > 0) {
       // edge stream
-      k_edge_update1<AT, kFast><<<cdiv(Mp, 16), 256, 0, s>>>(plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
+      ds_launch(k_edge_update1<AT, kFast>, dim3(cdiv(Mp, 16)), dim3(256), 0, s, plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
                                                             reinterpret_cast<AT*>(w.e1b));
       LAUNCH_CHECK(ctx);
       DS_TRY(linear(ctx, w.e1b, 64, bw.ff3_w, 64, bw.ff3_b, nullptr, 0, w.f3, 128, AD, Mp, 128, 64, ACT_SILU, s));
@@ -943,7 +987,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         DS_TRY(gemm_tc_launch(ctx, g, s));
       } else {
         DS_TRY(linear(ctx, w.f3, 128, bw.ff4_w, 128, bw.ff4_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
-        k_edge_update2<AT><<<cdiv(Mp, 8), 256, 0, s>>>(plan, w.e1f, w.y1, w.ada, l, w.e, X);
+        ds_launch(k_edge_update2<AT>, dim3(cdiv(Mp, 8)), dim3(256), 0, s, plan, w.e1f, w.y1, w.ada, l, w.e, X);
         LAUNCH_CHECK(ctx);
       }
       // equivariant coordinate update
@@ -953,7 +997,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         // whole coordinate head in one kernel: the LN+modulate operand never leaves the SM
         DS_TRY(coord_fused_launch(ctx, plan, w.ab, w.gp, ada_l, w.pflags, bw.wc1, bw.bc1, bw.wc2, w.wdir, s));
       } else {
-      k_coord_ln<AT, kFast><<<cdiv(Mn, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.ab), reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
+      ds_launch(k_coord_ln<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.ab), reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
                                                         reinterpret_cast<AT*>(w.Z), dflags);
       LAUNCH_CHECK(ctx);
       if (kFast && (ctx->fuse_mask & 8)) {
@@ -963,12 +1007,12 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         DS_TRY(gemm_tc_launch(ctx, g, s));
       } else {
         DS_TRY(linear(ctx, w.Z, 256, bw.wc1, 256, bw.bc1, nullptr, 0, w.u1, 256, AD, Md, 256, 256, kFast ? ACT_SILU_HALF : ACT_SILU, s));
-        k_coord_out<AT, kFast><<<cdiv(Md, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.u1), bw.wc2, dflags, w.wdir);
+        ds_launch(k_coord_out<AT, kFast>, dim3(cdiv(Md, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.u1), bw.wc2, dflags, w.wdir);
         LAUNCH_CHECK(ctx);
       }
       }
     }
-    k_pos_update<<<B, 64, 0, s>>>(plan, w.wdir, bw.coord_scale, w.pos);
+    ds_launch(k_pos_update, dim3(B), dim3(64), 0, s, plan, w.wdir, bw.coord_scale, w.pos);
     LAUNCH_CHECK(ctx);
     // skip connections into the prediction heads (dmt.py:387-388)
     DS_TRY(linear(ctx, w.hb, 256, bw.node_w, 256, bw.node_b, nullptr, 0, reinterpret_cast<AT*>(w.ahid) + 256 + 64 * l, 768,
@@ -981,7 +1025,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
   // prediction heads (dmt.py:391-399)
   DS_TRY(linear(ctx, w.ahid, 768, pw.np0_w, 768, pw.np0_b, nullptr, 0, w.n1, 256, AD, Mn, 256, 768, ACT_SILU, s));
   DS_TRY(linear(ctx, w.n1, 256, pw.np2_w, 256, pw.np2_b, nullptr, 0, w.n2, 128, AD, Mn, 128, 256, ACT_SILU, s));
-  k_node_head_out<AT><<<cdiv(Mn, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.n2), pw.np4_w, pw.np4_b, pred_x);
+  ds_launch(k_node_head_out<AT>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.n2), pw.np4_w, pw.np4_b, pred_x);
   LAUNCH_CHECK(ctx);
   if (Mp > 0) {
     DS_TRY(linear(ctx, w.ehid, 192, pw.eh0_w, 192, pw.eh0_b, nullptr, 0, w.eh1, 128, AD, Mp, 128, 192, ACT_SILU, s));
@@ -991,14 +1035,14 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       g.a_dtype = DT_BF16; g.mode = GEMM_EHEAD; g.wc2 = pw.eh4_wb; g.wdir = pred_e;
       DS_TRY(gemm_tc_launch(ctx, g, s));
     } else {
-      k_edge_head_out<AT, kFast><<<cdiv(Mp, 8), 256, 0, s>>>(plan, reinterpret_cast<const AT*>(w.eh1), pw.eh2t_w, pw.eh2_b,
+      ds_launch(k_edge_head_out<AT, kFast>, dim3(cdiv(Mp, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.eh1), pw.eh2t_w, pw.eh2_b,
                                                              pw.eh4_w, pw.eh4_b, pred_e);
       LAUNCH_CHECK(ctx);
     }
   }
-  k_pos_nan_flag<<<cdiv(Mn * 3, 256), 256, 0, s>>>(Mn, w.pos, w.flags);
+  ds_launch(k_pos_nan_flag, dim3(cdiv(Mn * 3, 256)), dim3(256), 0, s, Mn, w.pos, w.flags);
   LAUNCH_CHECK(ctx);
-  k_pos_final<<<B, 64, 0, s>>>(plan, w.pos, w.flags, pred_x);
+  ds_launch(k_pos_final, dim3(B), dim3(64), 0, s, plan, w.pos, w.flags, pred_x);
   LAUNCH_CHECK(ctx);
   return DS_OK;
 }

@@ -9,6 +9,8 @@ constexpr int TM = 64, TN = 64, TK = 16;
 
 template <typename TA, bool kFast>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmDesc g) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float As[TK][TM + 4];
   __shared__ float Ws[TK][TN + 4];
   const TA* __restrict__ A = reinterpret_cast<const TA*>(g.A);
@@ -78,14 +80,14 @@ int gemm_simt_launch(const GemmDesc& g, bool fast_math, cudaStream_t s) {
   dim3 grid((g.M + TM - 1) / TM, (g.N + TN - 1) / TN);
   if (g.a_dtype == DT_BF16) {
     if (fast_math)
-      gemm_simt_kernel<bf16, true><<<grid, 256, 0, s>>>(g);
+      ds_launch(gemm_simt_kernel<bf16, true>, dim3(grid), dim3(256), 0, s, g);
     else
-      gemm_simt_kernel<bf16, false><<<grid, 256, 0, s>>>(g);
+      ds_launch(gemm_simt_kernel<bf16, false>, dim3(grid), dim3(256), 0, s, g);
   } else {
     if (fast_math)
-      gemm_simt_kernel<float, true><<<grid, 256, 0, s>>>(g);
+      ds_launch(gemm_simt_kernel<float, true>, dim3(grid), dim3(256), 0, s, g);
     else
-      gemm_simt_kernel<float, false><<<grid, 256, 0, s>>>(g);
+      ds_launch(gemm_simt_kernel<float, false>, dim3(grid), dim3(256), 0, s, g);
   }
   DS_CUDA_CHECK(cudaGetLastError());
   return DS_OK;

@@ -158,6 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using C = Cfg<BN, MODE, TMA_OUT>;
   // 1024-byte alignment is requested from the compiler/driver (no static shared memory in this kernel), so plain
   // pointer arithmetic keeps the shared address space visible and the epilogues compile to LDS/STS, not generic LD/ST.
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   uint8_t* smA = smem;
@@ -206,6 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above (barriers, TMEM, weight-only reads) overlapped the predecessor's tail
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -499,7 +501,7 @@ int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  gemm_tc_kernel<BN, MODE, TMA_OUT><<<grid, kThreads, C::kSmemBytes, s>>>(tmA, tmW, tmO, tmR, tmF, ep, g.M, g.N, g.K);
+  ds_launch(gemm_tc_kernel<BN, MODE, TMA_OUT>, dim3(grid), dim3(kThreads), C::kSmemBytes, s, tmA, tmW, tmO, tmR, tmF, ep, g.M, g.N, g.K);
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;
   return DS_OK;

@@ -60,6 +60,8 @@ __device__ __forceinline__ float2 philox_pair(unsigned long long seed, long long
 
 // ----------------------------------------------------------------------------- dense <-> packed
 __global__ void k_pack_nodes(Plan plan, const float* __restrict__ x, float* __restrict__ xs) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= plan.Mn * 9) return;
   const int m = idx / 9, c = idx % 9;
@@ -68,6 +70,8 @@ __global__ void k_pack_nodes(Plan plan, const float* __restrict__ x, float* __re
   xs[idx] = x[(static_cast<size_t>(mol) * plan.N + a) * 9 + c];
 }
 __global__ void k_pack_pairs(Plan plan, const float* __restrict__ ex, float* __restrict__ es) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= plan.Mp * 2) return;
   const int p = idx >> 1, c = idx & 1;
@@ -76,12 +80,16 @@ __global__ void k_pack_pairs(Plan plan, const float* __restrict__ ex, float* __r
   es[idx] = ex[((static_cast<size_t>(mol) * plan.N + i) * plan.N + j) * 2 + c];
 }
 __global__ void k_unpack_nodes(Plan plan, const float* __restrict__ xs, float* __restrict__ x) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= plan.B * plan.N * 9) return;
   const int c = idx % 9, a = (idx / 9) % plan.N, mol = idx / (9 * plan.N);
   x[idx] = (a < plan.n_atoms[mol]) ? xs[static_cast<size_t>(plan.noff[mol] + a) * 9 + c] : 0.f;
 }
 __global__ void k_unpack_pairs(Plan plan, const float* __restrict__ es, float* __restrict__ ex) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(plan.B) * plan.N * plan.N * 2;
   if (idx >= total) return;
@@ -102,6 +110,8 @@ __global__ void k_unpack_pairs(Plan plan, const float* __restrict__ es, float* _
 __global__ void __launch_bounds__(256) k_sampler_nodes(Plan plan, float* __restrict__ xs, const float* __restrict__ pred,
                                                        float* __restrict__ xmean, StepRef sr, int step_host, NoiseSrc ns,
                                                        float temperature, int init_only) {
+  pdl_trigger();
+  pdl_wait();
   const int mol = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (mol >= plan.B) return;
   const int n = plan.n_atoms[mol], base = plan.noff[mol];
@@ -159,6 +169,8 @@ __global__ void __launch_bounds__(256) k_sampler_nodes(Plan plan, float* __restr
 __global__ void __launch_bounds__(256) k_sampler_pairs(Plan plan, float* __restrict__ es, const float* __restrict__ pred_e,
                                                        float* __restrict__ emean, StepRef sr, int step_host, NoiseSrc ns,
                                                        float temperature, int init_only) {
+  pdl_trigger();
+  pdl_wait();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= plan.Mp) return;
   const uint32_t info = plan.pair_info[p];
@@ -192,12 +204,16 @@ __global__ void __launch_bounds__(256) k_sampler_pairs(Plan plan, float* __restr
 }
 
 __global__ void k_step_inc(int* step) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0) *step += 1;
 }
 
 // ----------------------------------------------------------------------------- post_process (sampling.py:53-97)
 __global__ void k_post_nodes(Plan plan, const float* __restrict__ xs, float* __restrict__ pos, int* __restrict__ atom_type,
                              int* __restrict__ fc) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= plan.B * plan.N) return;
   const int a = idx % plan.N, mol = idx / plan.N;
@@ -218,6 +234,8 @@ __global__ void k_post_nodes(Plan plan, const float* __restrict__ xs, float* __r
   fc[idx] = q;
 }
 __global__ void k_post_pairs(Plan plan, const float* __restrict__ es, float* __restrict__ bond) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(plan.B) * plan.N * plan.N;
   if (idx >= total) return;
@@ -239,11 +257,11 @@ __global__ void k_post_pairs(Plan plan, const float* __restrict__ es, float* __r
 
 int launch_pack_dense(DsContext* ctx, const Plan& plan, const float* x, const float* ex, float* xs, float* es, cudaStream_t s) {
   if (x) {
-    k_pack_nodes<<<cdiv(plan.Mn * 9, 256), 256, 0, s>>>(plan, x, xs);
+    ds_launch(k_pack_nodes, dim3(cdiv(plan.Mn * 9, 256)), dim3(256), 0, s, plan, x, xs);
     LAUNCH_CHECK(ctx);
   }
   if (ex && plan.Mp > 0) {
-    k_pack_pairs<<<cdiv(plan.Mp * 2, 256), 256, 0, s>>>(plan, ex, es);
+    ds_launch(k_pack_pairs, dim3(cdiv(plan.Mp * 2, 256)), dim3(256), 0, s, plan, ex, es);
     LAUNCH_CHECK(ctx);
   }
   return DS_OK;
@@ -251,12 +269,12 @@ int launch_pack_dense(DsContext* ctx, const Plan& plan, const float* x, const fl
 
 int launch_unpack_dense(DsContext* ctx, const Plan& plan, const float* xs, const float* es, float* x, float* ex, cudaStream_t s) {
   if (x) {
-    k_unpack_nodes<<<cdiv(plan.B * plan.N * 9, 256), 256, 0, s>>>(plan, xs, x);
+    ds_launch(k_unpack_nodes, dim3(cdiv(plan.B * plan.N * 9, 256)), dim3(256), 0, s, plan, xs, x);
     LAUNCH_CHECK(ctx);
   }
   if (ex) {
     const size_t total = static_cast<size_t>(plan.B) * plan.N * plan.N * 2;
-    k_unpack_pairs<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(plan, es, ex);
+    ds_launch(k_unpack_pairs, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, plan, es, ex);
     LAUNCH_CHECK(ctx);
   }
   return DS_OK;
@@ -265,10 +283,10 @@ int launch_unpack_dense(DsContext* ctx, const Plan& plan, const float* xs, const
 int launch_sampler_step(DsContext* ctx, const Plan& plan, float* xs, float* es, const float* pred_x, const float* pred_e,
                         float* xmean, float* emean, StepRef sr, int step_host, const NoiseSrc& ns, float temperature,
                         cudaStream_t s) {
-  k_sampler_nodes<<<cdiv(plan.B, 8), 256, 0, s>>>(plan, xs, pred_x, xmean, sr, step_host, ns, temperature, 0);
+  ds_launch(k_sampler_nodes, dim3(cdiv(plan.B, 8)), dim3(256), 0, s, plan, xs, pred_x, xmean, sr, step_host, ns, temperature, 0);
   LAUNCH_CHECK(ctx);
   if (plan.Mp > 0) {
-    k_sampler_pairs<<<cdiv(plan.Mp, 256), 256, 0, s>>>(plan, es, pred_e, emean, sr, step_host, ns, temperature, 0);
+    ds_launch(k_sampler_pairs, dim3(cdiv(plan.Mp, 256)), dim3(256), 0, s, plan, es, pred_e, emean, sr, step_host, ns, temperature, 0);
     LAUNCH_CHECK(ctx);
   }
   return DS_OK;
@@ -276,27 +294,27 @@ int launch_sampler_step(DsContext* ctx, const Plan& plan, float* xs, float* es, 
 
 int launch_init_noise(DsContext* ctx, const Plan& plan, float* xs, float* es, const NoiseSrc& ns, cudaStream_t s) {
   StepRef sr{nullptr, nullptr};
-  k_sampler_nodes<<<cdiv(plan.B, 8), 256, 0, s>>>(plan, xs, nullptr, nullptr, sr, 0, ns, 1.0f, 1);
+  ds_launch(k_sampler_nodes, dim3(cdiv(plan.B, 8)), dim3(256), 0, s, plan, xs, nullptr, nullptr, sr, 0, ns, 1.0f, 1);
   LAUNCH_CHECK(ctx);
   if (plan.Mp > 0) {
-    k_sampler_pairs<<<cdiv(plan.Mp, 256), 256, 0, s>>>(plan, es, nullptr, nullptr, sr, 0, ns, 1.0f, 1);
+    ds_launch(k_sampler_pairs, dim3(cdiv(plan.Mp, 256)), dim3(256), 0, s, plan, es, nullptr, nullptr, sr, 0, ns, 1.0f, 1);
     LAUNCH_CHECK(ctx);
   }
   return DS_OK;
 }
 
 int launch_step_inc(DsContext* ctx, int* step, cudaStream_t s) {
-  k_step_inc<<<1, 32, 0, s>>>(step);
+  ds_launch(k_step_inc, dim3(1), dim3(32), 0, s, step);
   LAUNCH_CHECK(ctx);
   return DS_OK;
 }
 
 int launch_post_process(DsContext* ctx, const Plan& plan, const float* xs, const float* es, float* pos, int* atom_type,
                         int* fc, float* bond, cudaStream_t s) {
-  k_post_nodes<<<cdiv(plan.B * plan.N, 256), 256, 0, s>>>(plan, xs, pos, atom_type, fc);
+  ds_launch(k_post_nodes, dim3(cdiv(plan.B * plan.N, 256)), dim3(256), 0, s, plan, xs, pos, atom_type, fc);
   LAUNCH_CHECK(ctx);
   const size_t total = static_cast<size_t>(plan.B) * plan.N * plan.N;
-  k_post_pairs<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(plan, es, bond);
+  ds_launch(k_post_pairs, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, plan, es, bond);
   LAUNCH_CHECK(ctx);
   return DS_OK;
 }
