@@ -46,6 +46,19 @@ int ds_create(ds_ctx** out, int device, int mode, int spectra_version) {
   c->num_sms = prop.multiProcessorCount;
   if (const char* fm = getenv("DS_FUSE_MASK")) c->fuse_mask = atoi(fm);
   if (const char* pd = getenv("DS_PDL")) g_ds_use_pdl = atoi(pd) != 0;
+  if (const char* ov = getenv("DS_OVERLAP")) c->overlap = atoi(ov);
+  if (const char* sp = getenv("DS_SPLIT")) sscanf(sp, "%d,%d", &c->edge_cap, &c->node_cap);
+  if (c->edge_cap < 1 || c->node_cap < 1 || c->edge_cap + c->node_cap > prop.multiProcessorCount) {
+    c->edge_cap = prop.multiProcessorCount * 5 / 6;
+    c->node_cap = prop.multiProcessorCount - c->edge_cap;
+  }
+  if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    ds_set_error("ds_create: cannot create the side stream / events");
+    ds_ctx_free(c);
+    return DS_ERR_CUDA;
+  }
   int r = gemm_tc_init(c);
   if (r != DS_OK) {
     ds_ctx_free(c);
@@ -60,6 +73,9 @@ int ds_destroy(ds_ctx* h) {
   if (!c) return DS_OK;
   if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
   if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   ds_ctx_free(c);
   return DS_OK;
 }

@@ -15,6 +15,15 @@ struct DsContext {
   int num_sms = 148;
   void* encode_tiled = nullptr;      // cuTensorMapEncodeTiled (driver entry point, resolved at run time)
   int fuse_mask = 15;                // debug: bit0 LNMOD, bit1 RESGATE(node), bit2 RESGATE(edge), bit3 COORD epilogue, bit4 fused coordinate head (coord_tc.cu; off: measured slower than k_coord_ln + COORD GEMM)
+  // node-chain / edge-chain overlap inside a block (dmt_kernels.cu): the atom-side kernels (18 k rows, one tile per
+  // SM, latency-bound) run on a side stream next to the pair-side kernels; persistent GEMM grids are capped so that
+  // both fit on the 148 SMs at once.  Opt-in experiment: DS_OVERLAP=1 enables, DS_SPLIT=edge,node sets the caps.
+  int overlap = 0;                   // measured on B200: 455.9 ms / 100 steps without, 462-724 ms with (split 100,48 .. 140,8): the atom chain is
+                                     // throughput-, not latency-bound, so a branch only takes SMs away from the pair chain
+  int edge_cap = 124, node_cap = 24;
+  int cta_cap = 0;                   // cap applied to the next persistent-GEMM launches (0 = all SMs)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   long long launch_count = 0;        // kernels launched (or captured) through this context
   // cached CUDA graph of one sampling step (ds_sample_loop)
   cudaGraphExec_t step_graph = nullptr;

@@ -925,11 +925,33 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
   const int ngrp = (plan.N + ATT_G - 1) / ATT_G;
   uint8_t* dflags = w.pflags + (Mp > 0 ? Mp : 1);      // adjacency bits per directed edge (source-major order)
 
+  // Two chains per block share nothing until they meet (attention, coordinate head): the atom-side kernels go to a
+  // side stream (graph branch) with a small persistent-GEMM grid, the pair-side kernels keep the rest of the SMs.
+  const bool ov = kFast && ctx->overlap && ctx->side_stream != nullptr && Mp > 0;
+  cudaStream_t se = s, sn = ov ? ctx->side_stream : s;
+  const int ecap = ov ? ctx->edge_cap : 0, ncap = ov ? ctx->node_cap : 0;
+  auto fork = [&]() -> int {
+    if (!ov) return DS_OK;
+    DS_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
+    DS_CUDA_CHECK(cudaStreamWaitEvent(sn, ctx->ev_fork, 0));
+    return DS_OK;
+  };
+  auto join = [&]() -> int {
+    ctx->cta_cap = 0;
+    if (!ov) return DS_OK;
+    DS_CUDA_CHECK(cudaEventRecord(ctx->ev_join, sn));
+    DS_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    return DS_OK;
+  };
+
   for (int l = 0; l < N_LAYERS; ++l) {
     const BlockWeights& bw = pw.blk[l];
     const float* ada_l = w.ada + l * ADA_BLK;
+    DS_TRY(fork());
+    // ---- pair chain A: RBF -> edge_emb + LN + modulate -> lin_edge0 | lin_edge1
+    ctx->cta_cap = ecap;
     if (Mp > 0) {
-      ds_launch(k_rbf<AT, kFast>, dim3(cdiv(Mp, 128)), dim3(256), 0, s, plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
+      ds_launch(k_rbf<AT, kFast>, dim3(cdiv(Mp, 128)), dim3(256), 0, se, plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
       LAUNCH_CHECK(ctx);
       if (kFast && (ctx->fuse_mask & 1)) {
         // edge_emb -> LayerNorm -> modulate fused in the GEMM epilogue
@@ -937,17 +959,20 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         g.A = X; g.lda = 128; g.W = bw.edge_emb_w; g.ldw = 128; g.bias = bw.edge_emb_b; g.out = w.ea; g.ldo = 64;
         g.M = Mp; g.N = 64; g.K = 128; g.a_dtype = DT_BF16; g.out_dtype = DT_BF16; g.mode = GEMM_LNMOD;
         g.row_info = plan.pair_info; g.info_shift = 12; g.ada = ada_l; g.off_a = ADA_EDGE; g.off_b = ADA_EDGE + 64;
-        DS_TRY(gemm_tc_launch(ctx, g, s));
+        DS_TRY(gemm_tc_launch(ctx, g, se));
       } else {
-        DS_TRY(linear(ctx, X, 128, bw.edge_emb_w, 128, bw.edge_emb_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
-        ds_launch(k_pair_ln1<AT, kFast>, dim3(cdiv(Mp, 8)), dim3(256), 0, s, plan, w.y1, w.ada, l, reinterpret_cast<AT*>(w.ea));
+        DS_TRY(linear(ctx, X, 128, bw.edge_emb_w, 128, bw.edge_emb_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, se));
+        ds_launch(k_pair_ln1<AT, kFast>, dim3(cdiv(Mp, 8)), dim3(256), 0, se, plan, w.y1, w.ada, l, reinterpret_cast<AT*>(w.ea));
         LAUNCH_CHECK(ctx);
       }
-      DS_TRY(linear(ctx, w.ea, 64, bw.w01, 64, nullptr, nullptr, 0, w.e01, E01_LD, AD, Mp, E01_LD, 64, ACT_TANH, s));
+      DS_TRY(linear(ctx, w.ea, 64, bw.w01, 64, nullptr, nullptr, 0, w.e01, E01_LD, AD, Mp, E01_LD, 64, ACT_TANH, se));
     }
-    ds_launch(k_node_ln1<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, w.h, w.ada, l, reinterpret_cast<AT*>(w.hh));
+    // ---- atom chain A: LN + modulate -> q | k | v
+    ctx->cta_cap = ncap;
+    ds_launch(k_node_ln1<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, sn, plan, w.h, w.ada, l, reinterpret_cast<AT*>(w.hh));
     LAUNCH_CHECK(ctx);
-    DS_TRY(linear(ctx, w.hh, 256, bw.wqkv, 256, bw.bqkv, nullptr, 0, w.qkv, QKV_LD, AD, Mn, QKV_LD, 256, ACT_NONE, s));
+    DS_TRY(linear(ctx, w.hh, 256, bw.wqkv, 256, bw.bqkv, nullptr, 0, w.qkv, QKV_LD, AD, Mn, QKV_LD, 256, ACT_NONE, sn));
+    DS_TRY(join());
     if (plan.N <= 32)
       ds_launch(k_attention_grp<AT, kFast, 32>, dim3(B * ngrp), dim3(256), 0, s, plan, ngrp, reinterpret_cast<const AT*>(w.qkv), reinterpret_cast<const AT*>(w.e01), w.pflags,
                                                               w.hn, reinterpret_cast<AT*>(w.hnb));
@@ -956,70 +981,77 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
                                                               w.hn, reinterpret_cast<AT*>(w.hnb));
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hnb, 256, bw.n2e_w, 256, nullptr, nullptr, 0, w.pn, 64, DT_F32, Mn, 64, 256, ACT_NONE, s));
-    // node stream
-    ds_launch(k_node_update1<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, w.h, w.hn, w.ada, l, w.h1, reinterpret_cast<AT*>(w.h1b));
+    DS_TRY(fork());
+    // ---- atom chain B: residual + LN -> FFN -> residual; hoisted h_row | h_col parts of input_lin; skip projection
+    ctx->cta_cap = ncap;
+    ds_launch(k_node_update1<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, sn, plan, w.h, w.hn, w.ada, l, w.h1, reinterpret_cast<AT*>(w.h1b));
     LAUNCH_CHECK(ctx);
-    DS_TRY(linear(ctx, w.h1b, 256, bw.ff1_w, 256, bw.ff1_b, nullptr, 0, w.f1, 512, AD, Mn, 512, 256, ACT_SILU, s));
+    DS_TRY(linear(ctx, w.h1b, 256, bw.ff1_w, 256, bw.ff1_b, nullptr, 0, w.f1, 512, AD, Mn, 512, 256, ACT_SILU, sn));
     if (kFast && (ctx->fuse_mask & 2)) {
       GemmDesc g;     // h = h1 + gate * FFN(h1), fp32 stream + bf16 copy from one epilogue
       g.A = w.f1; g.lda = 512; g.W = bw.ff2_w; g.ldw = 512; g.bias = bw.ff2_b; g.out = w.h; g.ldo = 256;
       g.M = Mn; g.N = 256; g.K = 512; g.a_dtype = DT_BF16; g.out_dtype = DT_F32; g.mode = GEMM_RESGATE;
       g.row_info = plan.node_info; g.info_shift = 6; g.ada = ada_l; g.off_a = ADA_NODE + 1280;
       g.resid = w.h1; g.ldres = 256; g.out2 = w.hb; g.ldo2 = 256;
-      DS_TRY(gemm_tc_launch(ctx, g, s));
+      DS_TRY(gemm_tc_launch(ctx, g, sn));
     } else {
-      DS_TRY(linear(ctx, w.f1, 512, bw.ff2_w, 512, bw.ff2_b, nullptr, 0, w.f2, 256, DT_F32, Mn, 256, 512, ACT_NONE, s));
-      ds_launch(k_node_update2<AT>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, w.h1, w.f2, w.ada, l, w.h, reinterpret_cast<AT*>(w.hb));
+      DS_TRY(linear(ctx, w.f1, 512, bw.ff2_w, 512, bw.ff2_b, nullptr, 0, w.f2, 256, DT_F32, Mn, 256, 512, ACT_NONE, sn));
+      ds_launch(k_node_update2<AT>, dim3(cdiv(Mn, 8)), dim3(256), 0, sn, plan, w.h1, w.f2, w.ada, l, w.h, reinterpret_cast<AT*>(w.hb));
       LAUNCH_CHECK(ctx);
     }
+    if (Mp > 0)
+      DS_TRY(linear(ctx, w.hb, 256, bw.wab, 256, bw.bab, nullptr, 0, w.ab, 512, AD, Mn, 512, 256, ACT_NONE, sn));
+    // skip connection into the atom head (dmt.py:387-388)
+    DS_TRY(linear(ctx, w.hb, 256, bw.node_w, 256, bw.node_b, nullptr, 0, reinterpret_cast<AT*>(w.ahid) + 256 + 64 * l, 768,
+                  AD, Mn, 64, 256, ACT_NONE, sn));
     if (Mp > 0) {
-      // edge stream
-      ds_launch(k_edge_update1<AT, kFast>, dim3(cdiv(Mp, 16)), dim3(256), 0, s, plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
+      // ---- pair chain B: residual + LN -> FFN -> residual; pair part of input_lin; skip projection
+      ctx->cta_cap = ecap;
+      ds_launch(k_edge_update1<AT, kFast>, dim3(cdiv(Mp, 16)), dim3(256), 0, se, plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
                                                             reinterpret_cast<AT*>(w.e1b));
       LAUNCH_CHECK(ctx);
-      DS_TRY(linear(ctx, w.e1b, 64, bw.ff3_w, 64, bw.ff3_b, nullptr, 0, w.f3, 128, AD, Mp, 128, 64, ACT_SILU, s));
+      DS_TRY(linear(ctx, w.e1b, 64, bw.ff3_w, 64, bw.ff3_b, nullptr, 0, w.f3, 128, AD, Mp, 128, 64, ACT_SILU, se));
       if (kFast && (ctx->fuse_mask & 4)) {
         GemmDesc g;   // e = e1 + gate * FFN(e1) -> fp32 stream and the [dist | e] operand
         g.A = w.f3; g.lda = 128; g.W = bw.ff4_w; g.ldw = 128; g.bias = bw.ff4_b; g.out = w.e; g.ldo = 64;
         g.M = Mp; g.N = 64; g.K = 128; g.a_dtype = DT_BF16; g.out_dtype = DT_F32; g.mode = GEMM_RESGATE;
         g.row_info = plan.pair_info; g.info_shift = 12; g.ada = ada_l; g.off_a = ADA_EDGE + 320;
         g.resid = w.e1f; g.ldres = 64; g.out2 = X + 64; g.ldo2 = 128;
-        DS_TRY(gemm_tc_launch(ctx, g, s));
+        DS_TRY(gemm_tc_launch(ctx, g, se));
       } else {
-        DS_TRY(linear(ctx, w.f3, 128, bw.ff4_w, 128, bw.ff4_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, s));
-        ds_launch(k_edge_update2<AT>, dim3(cdiv(Mp, 8)), dim3(256), 0, s, plan, w.e1f, w.y1, w.ada, l, w.e, X);
+        DS_TRY(linear(ctx, w.f3, 128, bw.ff4_w, 128, bw.ff4_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, se));
+        ds_launch(k_edge_update2<AT>, dim3(cdiv(Mp, 8)), dim3(256), 0, se, plan, w.e1f, w.y1, w.ada, l, w.e, X);
         LAUNCH_CHECK(ctx);
       }
-      // equivariant coordinate update
-      DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, s));
-      DS_TRY(linear(ctx, w.hb, 256, bw.wab, 256, bw.bab, nullptr, 0, w.ab, 512, AD, Mn, 512, 256, ACT_NONE, s));
+      DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, se));
+      // skip connection into the edge heads (dmt.py:387-388)
+      DS_TRY(linear(ctx, X + 64, 128, bw.edge_w, 64, bw.edge_b, nullptr, 0, reinterpret_cast<AT*>(w.ehid) + 64 + 16 * l,
+                    192, AD, Mp, 16, 64, ACT_NONE, se));
+    }
+    DS_TRY(join());
+    if (Mp > 0) {
+      // ---- equivariant coordinate update (needs both chains)
       if (kFast && (ctx->fuse_mask & 16)) {
         // whole coordinate head in one kernel: the LN+modulate operand never leaves the SM
         DS_TRY(coord_fused_launch(ctx, plan, w.ab, w.gp, ada_l, w.pflags, bw.wc1, bw.bc1, bw.wc2, w.wdir, s));
       } else {
-      ds_launch(k_coord_ln<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.ab), reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
-                                                        reinterpret_cast<AT*>(w.Z), dflags);
-      LAUNCH_CHECK(ctx);
-      if (kFast && (ctx->fuse_mask & 8)) {
-        GemmDesc g;   // coord_mlp.0 -> SiLU -> coord_mlp.2 -> tanh -> adjacency-weighted mean, all in the epilogue
-        g.A = w.Z; g.lda = 256; g.W = bw.wc1; g.ldw = 256; g.bias = bw.bc1; g.M = Md; g.N = 256; g.K = 256;
-        g.a_dtype = DT_BF16; g.mode = GEMM_COORD; g.wc2 = bw.wc2; g.pflags = dflags; g.wdir = w.wdir;
-        DS_TRY(gemm_tc_launch(ctx, g, s));
-      } else {
-        DS_TRY(linear(ctx, w.Z, 256, bw.wc1, 256, bw.bc1, nullptr, 0, w.u1, 256, AD, Md, 256, 256, kFast ? ACT_SILU_HALF : ACT_SILU, s));
-        ds_launch(k_coord_out<AT, kFast>, dim3(cdiv(Md, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.u1), bw.wc2, dflags, w.wdir);
+        ds_launch(k_coord_ln<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.ab), reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
+                  reinterpret_cast<AT*>(w.Z), dflags);
         LAUNCH_CHECK(ctx);
-      }
+        if (kFast && (ctx->fuse_mask & 8)) {
+          GemmDesc g;   // coord_mlp.0 -> SiLU -> coord_mlp.2 -> tanh -> adjacency-weighted mean, all in the epilogue
+          g.A = w.Z; g.lda = 256; g.W = bw.wc1; g.ldw = 256; g.bias = bw.bc1; g.M = Md; g.N = 256; g.K = 256;
+          g.a_dtype = DT_BF16; g.mode = GEMM_COORD; g.wc2 = bw.wc2; g.pflags = dflags; g.wdir = w.wdir;
+          DS_TRY(gemm_tc_launch(ctx, g, s));
+        } else {
+          DS_TRY(linear(ctx, w.Z, 256, bw.wc1, 256, bw.bc1, nullptr, 0, w.u1, 256, AD, Md, 256, 256, kFast ? ACT_SILU_HALF : ACT_SILU, s));
+          ds_launch(k_coord_out<AT, kFast>, dim3(cdiv(Md, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.u1), bw.wc2, dflags, w.wdir);
+          LAUNCH_CHECK(ctx);
+        }
       }
     }
     ds_launch(k_pos_update, dim3(B), dim3(64), 0, s, plan, w.wdir, bw.coord_scale, w.pos);
     LAUNCH_CHECK(ctx);
-    // skip connections into the prediction heads (dmt.py:387-388)
-    DS_TRY(linear(ctx, w.hb, 256, bw.node_w, 256, bw.node_b, nullptr, 0, reinterpret_cast<AT*>(w.ahid) + 256 + 64 * l, 768,
-                  AD, Mn, 64, 256, ACT_NONE, s));
-    if (Mp > 0)
-      DS_TRY(linear(ctx, X + 64, 128, bw.edge_w, 64, bw.edge_b, nullptr, 0, reinterpret_cast<AT*>(w.ehid) + 64 + 16 * l,
-                    192, AD, Mp, 16, 64, ACT_NONE, s));
   }
 
   // prediction heads (dmt.py:391-399)

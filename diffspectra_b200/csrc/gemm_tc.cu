@@ -500,7 +500,8 @@ int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
   ep.out2_present = g.out2 != nullptr;
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
-  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  const int sms = (ctx->cta_cap > 0 && ctx->cta_cap < ctx->num_sms) ? ctx->cta_cap : ctx->num_sms;
+  const int grid = tiles < sms ? tiles : sms;
   ds_launch(gemm_tc_kernel<BN, MODE, TMA_OUT>, dim3(grid), dim3(kThreads), C::kSmemBytes, s, tmA, tmW, tmO, tmR, tmF, ep, g.M, g.N, g.K);
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;
