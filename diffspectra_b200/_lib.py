@@ -13,6 +13,7 @@ DT_F32, DT_BF16 = 0, 1
 ACT_NONE, ACT_SILU, ACT_TANH, ACT_GELU = 0, 1, 2, 3
 MODE_FP32, MODE_BF16 = 0, 1
 SPECTRA_VERSIONS = {'uv': 0, 'ir': 1, 'raman': 2, 'allspectra': 3}
+MODEL_KINDS = {'DMT': 0, 'DMT_WO_EQ': 1}
 
 
 class DiffSpectraError(RuntimeError):

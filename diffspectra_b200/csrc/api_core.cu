@@ -26,7 +26,12 @@ const char* ds_last_error(void) { return g_err; }
 int ds_version(void) { return 100; }
 
 int ds_create(ds_ctx** out, int device, int mode, int spectra_version) {
+  return ds_create_model(out, device, mode, spectra_version, DS_MODEL_DMT);
+}
+
+int ds_create_model(ds_ctx** out, int device, int mode, int spectra_version, int model_kind) {
   DS_CHECK(out != nullptr, DS_ERR_INVALID, "ds_create: null out");
+  DS_CHECK(model_kind == DS_MODEL_DMT || model_kind == DS_MODEL_DMT_WO_EQ, DS_ERR_INVALID, "ds_create: unknown model kind %d", model_kind);
   DS_CHECK(mode == 0 || mode == 1, DS_ERR_INVALID, "ds_create: mode must be 0 (fp32) or 1 (bf16), got %d", mode);
   DS_CHECK(spectra_version >= 0 && spectra_version <= 3, DS_ERR_INVALID, "ds_create: bad spectra_version %d",
            spectra_version);
@@ -43,6 +48,7 @@ int ds_create(ds_ctx** out, int device, int mode, int spectra_version) {
   c->device = device;
   c->mode = mode;
   c->spectra_version = spectra_version;
+  c->model_kind = model_kind;
   c->num_sms = prop.multiProcessorCount;
   if (const char* fm = getenv("DS_FUSE_MASK")) c->fuse_mask = atoi(fm);
   if (const char* pd = getenv("DS_PDL")) g_ds_use_pdl = atoi(pd) != 0;

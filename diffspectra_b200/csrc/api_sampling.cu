@@ -28,7 +28,7 @@ inline CtxFull* full(ds_ctx* h) { return reinterpret_cast<CtxFull*>(h); }
 // plan blob layout (device, int32): n_atoms[B] | noff[B+1] | poff[B+1] | node_info[Mn_max] | pair_info[Mp_max] |
 // dir_info[2*Mp_max] (int4)
 struct PlanLayout {
-  size_t n_atoms, noff, poff, node_info, pair_info, dir_info, total;
+  size_t n_atoms, noff, poff, node_info, pair_info, dir_info, dir_mol, total;
 };
 PlanLayout plan_layout(int B, int N) {
   PlanLayout L;
@@ -40,6 +40,7 @@ PlanLayout plan_layout(int B, int N) {
   L.node_info = o; o = al(o + size_t(B) * N * 4);
   L.pair_info = o; o = al(o + size_t(B) * N * (N - 1) / 2 * 4 + 4);
   L.dir_info = o; o = al(o + size_t(B) * N * (N - 1) * 16 + 16);
+  L.dir_mol = o; o = al(o + size_t(B) * N * (N - 1) * 4 + 4);
   L.total = o;
   return L;
 }
@@ -55,6 +56,7 @@ int make_plan(const void* plan_dev, int B, int N, int Mn, int Mp, Plan* p) {
   p->node_info = reinterpret_cast<const uint32_t*>(base + L.node_info);
   p->pair_info = reinterpret_cast<const uint32_t*>(base + L.pair_info);
   p->dir_info = reinterpret_cast<const int4*>(base + L.dir_info);
+  p->dir_mol = reinterpret_cast<const uint32_t*>(base + L.dir_mol);
   return DS_OK;
 }
 
@@ -113,6 +115,7 @@ int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_d
   uint32_t* ni = reinterpret_cast<uint32_t*>(host.data() + L.node_info);
   uint32_t* pi = reinterpret_cast<uint32_t*>(host.data() + L.pair_info);
   int4* di = reinterpret_cast<int4*>(host.data() + L.dir_info);
+  uint32_t* dm = reinterpret_cast<uint32_t*>(host.data() + L.dir_mol);
   int mn = 0, mp = 0;
   for (int b = 0; b < B; ++b) {
     const int n = n_atoms_host[b];
@@ -129,7 +132,9 @@ int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_d
         if (c == r) continue;
         const int lo = r < c ? r : c, hi = r < c ? c : r;
         const int pr = mp + lo * n - (lo * (lo + 1)) / 2 + (hi - lo - 1);
-        di[static_cast<size_t>(2) * mp + static_cast<size_t>(r) * (n - 1) + (c - (c > r ? 1 : 0))] = make_int4(pr, mn + r, mn + c, b);
+        const size_t dd = static_cast<size_t>(2) * mp + static_cast<size_t>(r) * (n - 1) + (c - (c > r ? 1 : 0));
+        di[dd] = make_int4(pr, mn + r, mn + c, b);
+        dm[dd] = static_cast<uint32_t>(b);
       }
     mn += n;
     mp += n * (n - 1) / 2;
@@ -150,7 +155,7 @@ size_t ds_workspace_bytes(ds_ctx* h, int B, int Mn, int Mp) {
   Arena a{nullptr, 0, 0, true};
   DenoiseWs dw;
   LoopWs lw;
-  denoise_ws_carve(a, dw, B, Mn, Mp, ds_is_bf16(c));
+  denoise_ws_carve(a, dw, B, Mn, Mp, ds_is_bf16(c), c->model_kind);
   loop_ws_carve(a, lw, Mn, Mp);
   a.take(size_t(B) * D_TIME * 4);   // ctx embedding when the loop computes it
   return a.off + 1024;
@@ -197,7 +202,7 @@ int ds_denoise(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp, co
   Arena a{static_cast<uint8_t*>(workspace), 0, workspace_bytes, false};
   DenoiseWs dw;
   LoopWs lw;
-  denoise_ws_carve(a, dw, B, Mn, Mp, ds_is_bf16(c));
+  denoise_ws_carve(a, dw, B, Mn, Mp, ds_is_bf16(c), c->model_kind);
   loop_ws_carve(a, lw, Mn, Mp);
   DS_CHECK(a.off <= workspace_bytes, DS_ERR_WORKSPACE, "ds_denoise: workspace too small (%zu < %zu)", workspace_bytes, a.off);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -232,7 +237,7 @@ int ds_sample_loop(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp
   Arena a{static_cast<uint8_t*>(workspace), 0, workspace_bytes, false};
   DenoiseWs dw;
   LoopWs lw;
-  denoise_ws_carve(a, dw, B, Mn, Mp, ds_is_bf16(c));
+  denoise_ws_carve(a, dw, B, Mn, Mp, ds_is_bf16(c), c->model_kind);
   loop_ws_carve(a, lw, Mn, Mp);
   DS_CHECK(a.off <= workspace_bytes, DS_ERR_WORKSPACE, "ds_sample_loop: workspace too small (%zu < %zu)", workspace_bytes, a.off);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

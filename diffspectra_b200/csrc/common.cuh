@@ -177,6 +177,7 @@ struct Plan {
   // [2*Mp] directed edges, source-major (d = 2*poff[mol] + r*(n-1) + c - (c > r)):
   // x = pair row, y = atom row of the source r, z = atom row of the target c, w = molecule
   const int4* dir_info;
+  const uint32_t* dir_mol;     // [2*Mp] molecule of each directed edge (row_info form for the GEMM epilogues)
 };
 __device__ __forceinline__ int pair_index(int n, int i, int j) {   // i < j < n, row-major upper triangle
   return i * n - (i * (i + 1)) / 2 + (j - i - 1);

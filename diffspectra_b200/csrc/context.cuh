@@ -12,6 +12,7 @@ struct DsContext {
   int device = 0;
   int mode = 0;              // 0 = fp32 validation (SIMT GEMM, libm maths), 1 = bf16 production (tcgen05 GEMM)
   int spectra_version = 3;   // 0 uv, 1 ir, 2 raman, 3 allspectra
+  int model_kind = 0;        // 0 = DMT (models/dmt.py), 1 = DMT_WO_EQ ablation (models/dmt_wo_eq.py)
   int num_sms = 148;
   void* encode_tiled = nullptr;      // cuTensorMapEncodeTiled (driver entry point, resolved at run time)
   int fuse_mask = 15;                // debug: bit0 LNMOD, bit1 RESGATE(node), bit2 RESGATE(edge), bit3 COORD epilogue, bit4 fused coordinate head (coord_tc.cu; off: measured slower than k_coord_ln + COORD GEMM)

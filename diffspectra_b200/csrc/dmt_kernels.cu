@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(256) k_node_head_out(Plan plan, const AT* __re
 
 // edge_pred = [edge_exist_mlp, edge_type_mlp] layers 2 and 4 (dmt.py:394); layer 0 (both heads) is the GEMM eh1
 template <typename AT, bool kFast>
-__global__ void __launch_bounds__(256) k_edge_head_out(Plan plan, const AT* __restrict__ eh1, const float* __restrict__ w2t,
+__global__ void __launch_bounds__(256) k_edge_head_out(int rows, const AT* __restrict__ eh1, const float* __restrict__ w2t,
                                                        const float* __restrict__ b2, const float* __restrict__ w4,
                                                        const float* __restrict__ b4, float* __restrict__ pred_e) {
   pdl_trigger();
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(256) k_edge_head_out(Plan plan, const AT* __re
   __shared__ float row[8][128];
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.x * 8 + wi;
-  if (p >= plan.Mp) return;
+  if (p >= rows) return;
   const float4 v = load4<AT>(eh1 + static_cast<size_t>(p) * 128 + 4 * lane);
   row[wi][4 * lane + 0] = v.x; row[wi][4 * lane + 1] = v.y; row[wi][4 * lane + 2] = v.z; row[wi][4 * lane + 3] = v.w;
   __syncwarp();
@@ -1067,7 +1067,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       g.a_dtype = DT_BF16; g.mode = GEMM_EHEAD; g.wc2 = pw.eh4_wb; g.wdir = pred_e;
       DS_TRY(gemm_tc_launch(ctx, g, s));
     } else {
-      ds_launch(k_edge_head_out<AT, kFast>, dim3(cdiv(Mp, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.eh1), pw.eh2t_w, pw.eh2_b,
+      ds_launch(k_edge_head_out<AT, kFast>, dim3(cdiv(Mp, 8)), dim3(256), 0, s, Mp, reinterpret_cast<const AT*>(w.eh1), pw.eh2t_w, pw.eh2_b,
                                                              pw.eh4_w, pw.eh4_b, pred_e);
       LAUNCH_CHECK(ctx);
     }
@@ -1079,7 +1079,17 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
   return DS_OK;
 }
 
+#include "dmt_wo_eq.cuh"
+
 }  // namespace
+
+int denoise_wo_eq_packed(DsContext* ctx, const PackedWeights& pw, const Plan& plan, const float* xs, const float* es,
+                         const float* cond_x, const float* cond_e, const float* noise_level, StepRef sr, const float* ctx_emb,
+                         float* pred_x, float* pred_e, DenoiseWs& w, cudaStream_t s) {
+  if (ds_is_bf16(ctx))
+    return denoise_wo_impl<bf16, true>(ctx, pw, plan, xs, es, cond_x, cond_e, noise_level, sr, ctx_emb, pred_x, pred_e, w, s);
+  return denoise_wo_impl<float, false>(ctx, pw, plan, xs, es, cond_x, cond_e, noise_level, sr, ctx_emb, pred_x, pred_e, w, s);
+}
 
 int linear(DsContext* ctx, const void* A, int lda, const void* W, int ldw, const float* bias, const float* addmat,
            int ldadd, void* out, int ldo, int out_dtype, int M, int N, int K, int act, cudaStream_t s) {
@@ -1095,9 +1105,11 @@ int linear(DsContext* ctx, const void* A, int lda, const void* W, int ldw, const
   return gemm_simt_launch(g, ds_is_bf16(ctx), s);
 }
 
-size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf) {
+size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf, int model_kind) {
   const size_t es = bf ? 2 : 4;
-  const size_t mn = Mn > 0 ? Mn : 1, mp = Mp > 0 ? Mp : 1, md = 2 * mp, b = B;
+  // DMT_WO_EQ keeps every edge tensor per DIRECTED edge (its edges are not symmetric) and has no coordinate head
+  const bool wo = model_kind == 1;
+  const size_t mn = Mn > 0 ? Mn : 1, mp = (Mp > 0 ? Mp : 1) * (wo ? 2 : 1), md = wo ? 1 : 2 * mp, b = B;
   const size_t start = a.off;
   w.tfeat_f = nullptr;
   w.tfeat = a.take(b * D_TIME * es);
@@ -1136,6 +1148,9 @@ size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf) 
   w.u1 = a.take(md * 256 * es);
   w.wdir = static_cast<float*>(a.take(md * 4));
   w.flags = static_cast<int*>(a.take(16));
+  w.pab = wo ? static_cast<float*>(a.take(mn * 128 * 4)) : nullptr;
+  w.eb = wo ? a.take(mp * 64 * es) : nullptr;
+  w.pred_dir = wo ? static_cast<float*>(a.take(mp * 2 * 4)) : nullptr;
   return a.off - start;
 }
 
@@ -1145,6 +1160,8 @@ int denoise_packed(DsContext* ctx, const PackedWeights& pw, const Plan& plan, co
   DS_CHECK(pw.valid, DS_ERR_INVALID, "denoise: weights not packed (call ds_pack_weights first)");
   DS_CHECK(plan.Mn > 0, DS_ERR_INVALID, "denoise: empty plan");
   DS_CHECK((cond_x == nullptr) == (cond_e == nullptr), DS_ERR_INVALID, "denoise: cond_x and cond_edge_x must both be given or both null");
+  if (ctx->model_kind == 1)
+    return denoise_wo_eq_packed(ctx, pw, plan, xs, es, cond_x, cond_e, noise_level, sr, ctx_emb, pred_x, pred_e, w, s);
   if (ds_is_bf16(ctx))
     return denoise_impl<bf16, true>(ctx, pw, plan, xs, es, cond_x, cond_e, noise_level, sr, ctx_emb, pred_x, pred_e, w, s);
   return denoise_impl<float, false>(ctx, pw, plan, xs, es, cond_x, cond_e, noise_level, sr, ctx_emb, pred_x, pred_e, w, s);

@@ -27,6 +27,11 @@ struct BlockWeights {
   const float* rbf_stds;    // [63]
   const void* node_w; const float* node_b;   // node_l [64,256]
   const void* edge_w; const float* edge_b;   // edge_l [16,64]
+  // DMT_WO_EQ (models/dmt_wo_eq.py:200-202,436-441): wqkv = lin_qkv [768,256] in the reference's [head][q|k|v][16]
+  // order, n2e_b = node2edge_lin.bias
+  const void* wkve;         // lin_kv_e [512,64], [head][k|v][16]
+  const void* wproj; const float* bproj;   // proj [256,256]
+  const void* wn2e2;        // [128,256] rows 0..63 = node2edge_lin[:, 0:256] (source), 64..127 = [:, 256:512] (target)
 };
 
 struct SpecLayerWeights {
@@ -62,6 +67,12 @@ struct PackedWeights {
   const void* eh2_bd;                      // act [64,128] block-diagonal second layers (tensor-core path)
   const float* eh4_wb;                     // [66] = w4 exist | w4 type | b4 exist, b4 type
   const void* root_w;                      // act [64,128] root edge_emb for operand [d0 | edge_x cond_edge | 0]
+  // DMT_WO_EQ root / position head (models/dmt_wo_eq.py:629-643,709-717)
+  const float* wo_x_w; const float* wo_x_b;      // node_emb.x_linear [512,12]
+  const float* wo_pos_w; const float* wo_pos_b;  // node_emb.pos_linear [512,3]
+  const void* wo_mlp_w; const float* wo_mlp_b;   // node_emb.mlp.1 [256,512]
+  const void* wo_p0_w;                           // pos_pred_mlp.0 [256,768] (no bias)
+  const float* wo_p2_w;                          // pos_pred_mlp.2 [3,256] (no bias)
   // SpecFormer
   int n_spec = 0;                          // number of spectra used (1 or 3)
   int spec_type[3];                        // 0 uv, 1 ir, 2 raman
@@ -126,9 +137,13 @@ struct DenoiseWs {      // scratch of one denoiser call on a plan (sizes in elem
   void* u1;             // act [2Mp,256]
   float* wdir;          // [2Mp]
   int* flags;           // [4] 0: any cond distance non-zero, 1: NaN seen
+  // DMT_WO_EQ only (edge buffers above are then sized per DIRECTED edge)
+  float* pab;           // [Mn,128] node2edge_lin halves applied per atom: [W[:, :256] hn | W[:, 256:] hn]
+  void* eb;             // act [2Mp,64] copy of the edge stream
+  float* pred_dir;      // [2Mp,2] edge-head output per directed edge (symmetrised afterwards)
 };
 
-size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf16mode);
+size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf16mode, int model_kind);
 
 // ----------------------------------------------------------------------------- launchers
 int linear(DsContext* ctx, const void* A, int lda, const void* W, int ldw, const float* bias, const float* addmat,
@@ -143,6 +158,10 @@ struct StepRef {
 int denoise_packed(DsContext* ctx, const PackedWeights& pw, const Plan& plan, const float* xs, const float* es,
                    const float* cond_x, const float* cond_e, const float* noise_level, StepRef sr,
                    const float* ctx_emb, float* pred_x, float* pred_e, DenoiseWs& w, cudaStream_t s);
+// DMT_WO_EQ (dmt_wo_eq_kernels.cu); same contract
+int denoise_wo_eq_packed(DsContext* ctx, const PackedWeights& pw, const Plan& plan, const float* xs, const float* es,
+                         const float* cond_x, const float* cond_e, const float* noise_level, StepRef sr,
+                         const float* ctx_emb, float* pred_x, float* pred_e, DenoiseWs& w, cudaStream_t s);
 
 // fused coordinate head of one block (coord_tc.cu): LN+modulate operand built in shared memory -> tcgen05 -> w[d]
 int coord_fused_launch(DsContext* ctx, const Plan& plan, const void* ab, const void* gp, const float* ada_l,

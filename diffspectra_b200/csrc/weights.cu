@@ -71,8 +71,20 @@ struct Packer {
 
 int build(Packer& P, PackedWeights& pw) {
   DsContext* ctx = P.ctx;
-  pw.node_emb_w = P.vec("node_emb.weight", 256 * 12);
-  pw.node_emb_b = P.vec("node_emb.bias", 256);
+  const bool wo = ctx->model_kind == 1;      // DMT_WO_EQ parameter names (models/dmt_wo_eq.py:679-746)
+  if (!wo) {
+    pw.node_emb_w = P.vec("node_emb.weight", 256 * 12);
+    pw.node_emb_b = P.vec("node_emb.bias", 256);
+  } else {
+    pw.wo_x_w = P.vec("node_emb.x_linear.weight", 512 * 12);
+    pw.wo_x_b = P.vec("node_emb.x_linear.bias", 512);
+    pw.wo_pos_w = P.vec("node_emb.pos_linear.weight", 512 * 3);
+    pw.wo_pos_b = P.vec("node_emb.pos_linear.bias", 512);
+    pw.wo_mlp_w = P.mat("node_emb.mlp.1.weight", 256, 512);
+    pw.wo_mlp_b = P.vec("node_emb.mlp.1.bias", 256);
+    pw.wo_p0_w = P.mat("pos_pred_mlp.0.weight", 256, 768);
+    pw.wo_p2_w = P.vec("pos_pred_mlp.2.weight", 3 * 256);
+  }
   pw.edge_emb_w = P.vec("edge_emb.weight", 64 * 68);
   pw.edge_emb_b = P.vec("edge_emb.bias", 64);
   {   // tensor-core form of the root edge embedding: operand columns [d0(64) | edge_x(2) cond_edge(2) | 0...]
@@ -102,7 +114,41 @@ int build(Packer& P, PackedWeights& pw) {
   ada_rows("dist_layer.time_mlp.1", ADA_ROOT_RBF, 2);
 
   char buf[128];
-  for (int l = 0; l < N_LAYERS; ++l) {
+  for (int l = 0; wo && l < N_LAYERS; ++l) {
+    BlockWeights& b = pw.blk[l];
+    snprintf(buf, sizeof(buf), "dmt_block_%d.", l);
+    const std::string p(buf);
+    ada_rows(p + "node_time_mlp.1", l * ADA_BLK + ADA_NODE, 1536);
+    ada_rows(p + "edge_time_mlp.1", l * ADA_BLK + ADA_EDGE, 384);
+    b.wqkv = P.mat(p + "attn_mpnn.lin_qkv.weight", 768, 256);
+    b.bqkv = P.vec(p + "attn_mpnn.lin_qkv.bias", 768);
+    b.wkve = P.mat(p + "attn_mpnn.lin_kv_e.weight", 512, 64);
+    b.wproj = P.mat(p + "attn_mpnn.proj.weight", 256, 256);
+    b.bproj = P.vec(p + "attn_mpnn.proj.bias", 256);
+    {   // node2edge_lin [64,512] acts on cat[hn_r, hn_c]: applied per atom as two 256 -> 64 projections
+      const float* w = P.get(p + "node2edge_lin.weight");
+      void* w2 = P.alloc_act(128 * 256);
+      P.copy(w, 512, w2, 0, 256, 64, 256, true);
+      P.copy(w ? w + 256 : nullptr, 512, w2, 64 * 256, 256, 64, 256, true);
+      b.wn2e2 = w2;
+      b.n2e_b = P.vec(p + "node2edge_lin.bias", 64);
+    }
+    b.ff1_w = P.mat(p + "ff_linear1.weight", 512, 256);
+    b.ff1_b = P.vec(p + "ff_linear1.bias", 512);
+    b.ff2_w = P.mat(p + "ff_linear2.weight", 256, 512);
+    b.ff2_b = P.vec(p + "ff_linear2.bias", 256);
+    b.ff3_w = P.mat(p + "ff_linear3.weight", 128, 64);
+    b.ff3_b = P.vec(p + "ff_linear3.bias", 128);
+    b.ff4_w = P.mat(p + "ff_linear4.weight", 64, 128);
+    b.ff4_b = P.vec(p + "ff_linear4.bias", 64);
+    snprintf(buf, sizeof(buf), "node_%d", l);
+    b.node_w = P.mat(std::string(buf) + ".weight", 64, 256);
+    b.node_b = P.vec(std::string(buf) + ".bias", 64);
+    snprintf(buf, sizeof(buf), "edge_%d", l);
+    b.edge_w = P.mat(std::string(buf) + ".weight", 16, 64);
+    b.edge_b = P.vec(std::string(buf) + ".bias", 16);
+  }
+  for (int l = 0; !wo && l < N_LAYERS; ++l) {
     BlockWeights& b = pw.blk[l];
     snprintf(buf, sizeof(buf), "e_block_%d.", l);
     const std::string p(buf);

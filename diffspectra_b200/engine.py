@@ -33,7 +33,7 @@ class Plan:
 
 
 class Engine:
-    def __init__(self, device, mode='bf16', spectra_version='allspectra'):
+    def __init__(self, device, mode='bf16', spectra_version='allspectra', model_kind='DMT'):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise L.DiffSpectraError('diffspectra_b200 runs on a CUDA (sm_100a) device only; got %s — there is no CPU '
@@ -41,10 +41,12 @@ class Engine:
         self.mode = {'fp32': L.MODE_FP32, 'bf16': L.MODE_BF16}[mode]
         self.mode_name = mode
         self.spectra_version = spectra_version
+        self.model_kind = model_kind
         self.h = ctypes.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         with torch.cuda.device(idx):
-            L.check(L.lib().ds_create(ctypes.byref(self.h), idx, self.mode, L.SPECTRA_VERSIONS[spectra_version]), 'ds_create')
+            L.check(L.lib().ds_create_model(ctypes.byref(self.h), idx, self.mode, L.SPECTRA_VERSIONS[spectra_version],
+                                            L.MODEL_KINDS[model_kind]), 'ds_create_model')
         self.blob = None
         self._ws = None
         self._spec_ws = None

@@ -172,48 +172,16 @@ def _mlp3(i, h1, h2, o):
     return nn.Sequential(nn.Linear(i, h1), nn.SiLU(), nn.Linear(h1, h2), nn.SiLU(), nn.Linear(h2, o))
 
 
-# ----------------------------------------------------------------------------- the module
-class DMT_B200(nn.Module):
-    """Conditional Diffusion Molecule Transformer with self-conditioning, B200-native forward."""
+# ----------------------------------------------------------------------------- the modules
+class _B200Denoiser(nn.Module):
+    """Engine plumbing + the reference call signature shared by DMT_B200 and DMT_WO_EQ_B200.  Sub-classes only
+    register parameters (same names / shapes / order as the reference class) and set MODEL_KIND."""
+    MODEL_KIND = 'DMT'
 
-    def __init__(self, config):
-        super().__init__()
-        m, d = config.model, config.data
-        in_node_dim = d.atom_types + int(m.include_fc_charge)
-        hidden_dim = m.nf
-        edge_hidden_dim = m.nf // 4
-        n_layers = m.n_layers
-        time_dim = hidden_dim * 4
-        supported = (in_node_dim == 6 and hidden_dim == 256 and n_layers == 8 and m.n_heads == 16 and
-                     m.n_extra_heads == 2 and m.mlp_ratio == 2 and m.edge_ch == 2 and m.dist_gbf and m.cond_time and
-                     m.pred_data and m.CoM and m.softmax_inf and m.gbf_name == 'CondGaussianLayer' and
-                     float(m.spatial_cut_off) == 2.0 and float(m.edge_quan_th) == 0.0 and
-                     list(m.patch_len) == [20, 50, 50] and list(m.stride) == [10, 25, 25])
-        if not supported:
-            raise ValueError('DMT_B200 kernels are specialised for the QM9S DiffSpectra configuration '
-                             '(configs/diffspectra_qm9s.py:44-76); got a different model config')
-        self.n_layers = n_layers
-        self.spectra_version = d.spectra_version
-        self.precision = _cfg(m, 'b200_precision', 'bf16')          # 'bf16' (tcgen05) | 'fp32' (validation)
-
-        self.node_emb = nn.Linear(in_node_dim * 2, hidden_dim)
-        self.edge_emb = nn.Linear(m.edge_ch * 2 + edge_hidden_dim, edge_hidden_dim)
-        self.dist_layer = _CondGaussianParams(edge_hidden_dim, time_dim)
-        cat_node_dim = (hidden_dim * 2) // n_layers
-        cat_edge_dim = (edge_hidden_dim * 2) // n_layers
-        for i in range(n_layers):
-            self.add_module('e_block_%d' % i, _BlockParams(hidden_dim, edge_hidden_dim, time_dim, m.n_extra_heads,
-                                                           m.n_heads, m.mlp_ratio))
-            self.add_module('node_%d' % i, nn.Linear(hidden_dim, cat_node_dim))
-            self.add_module('edge_%d' % i, nn.Linear(edge_hidden_dim, cat_edge_dim))
-        self.node_pred_mlp = _mlp3(cat_node_dim * n_layers + hidden_dim, hidden_dim, hidden_dim // 2, in_node_dim)
-        self.edge_type_mlp = _mlp3(cat_edge_dim * n_layers + edge_hidden_dim, edge_hidden_dim, edge_hidden_dim // 2,
-                                   m.edge_ch - 1)
-        self.edge_exist_mlp = _mlp3(cat_edge_dim * n_layers + edge_hidden_dim, edge_hidden_dim, edge_hidden_dim // 2, 1)
-        self.time_mlp = nn.Sequential(_SinEmbParams(16), nn.Linear(17, time_dim), nn.GELU(), nn.Linear(time_dim, time_dim))
-        self.cond_encoder = _SpecFormerParams(m.patch_len, m.stride, hidden_dim, d.spectra_version)
-        self.cond_lin = nn.Linear(hidden_dim, time_dim)
-        if _cfg(m, 'pretrained_specformer_path', ''):
+    def _init_plumbing(self, config):
+        self.spectra_version = config.data.spectra_version
+        self.precision = _cfg(config.model, 'b200_precision', 'bf16')          # 'bf16' (tcgen05) | 'fp32' (validation)
+        if _cfg(config.model, 'pretrained_specformer_path', ''):
             raise NotImplementedError('pretrained SpecFormer loading (models/dmt.py:268-303) is outside the sampling '
                                       'hot path; load the full checkpoint instead')
         self._engine = None
@@ -228,7 +196,7 @@ class DMT_B200(nn.Module):
     def engine(self, device=None):
         device = torch.device(device) if device is not None else next(self.parameters()).device
         if self._engine is None or self._engine.device != device or self._engine.mode_name != self.precision:
-            self._engine = Engine(device, mode=self.precision, spectra_version=self.spectra_version)
+            self._engine = Engine(device, mode=self.precision, spectra_version=self.spectra_version, model_kind=self.MODEL_KIND)
             self._weights_key = None
             self._plan_cache = {}
             self._ctx_cache = (None, None)
@@ -253,7 +221,8 @@ class DMT_B200(nn.Module):
             n_atoms = nm.sum(dim=1).round().to(torch.int32).cpu().numpy()
             # valid atoms must be a prefix (sampling.py:432-434)
             if not bool((nm[:, :1] > 0).all()) or not bool(((nm[:, 1:] - nm[:, :-1]) <= 0).all()):
-                raise ValueError('DMT_B200 expects prefix node masks (first n atoms valid) as built by sampling.py:432-434')
+                raise ValueError('%s expects prefix node masks (first n atoms valid) as built by sampling.py:432-434'
+                                 % type(self).__name__)
             plan = self._engine.plan(n_atoms, nm.shape[1])
             if len(self._plan_cache) > 8:
                 self._plan_cache.clear()
@@ -271,27 +240,142 @@ class DMT_B200(nn.Module):
 
     # ------------------------------------------------------------------ reference interface
     def forward(self, t, xh, node_mask, edge_mask, context=None, *args, **kwargs):
-        """Same contract as DMT.forward (models/dmt.py:306-321,413): returns ([B,N,9], [B,N,N,2]) fp32 on
-        xh.device; `t`, `alpha_t`, `sigma_t` are accepted and unused like in the reference."""
+        """Same contract as DMT.forward / DMT_WO_EQ.forward (models/dmt.py:306-321,413; models/dmt_wo_eq.py:811-829):
+        returns ([B,N,9], [B,N,N,2]) fp32 on xh.device; `t`, `alpha_t`, `sigma_t` are accepted and unused like in the
+        reference."""
         edge_x = kwargs['edge_x']
         cond_x, cond_edge_x = kwargs.get('cond_x'), kwargs.get('cond_edge_x')
         noise_level = kwargs['noise_level']
         if context is None:
-            raise ValueError('DMT_B200 is the spectra-conditioned denoiser: context must be given')
+            raise ValueError('%s is the spectra-conditioned denoiser: context must be given' % type(self).__name__)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError('DMT_B200 implements the inference (sampling) path only; wrap calls in '
-                                      'torch.no_grad() / model.eval() (training is out of scope, SURVEY.md §8(f).4)')
+            raise NotImplementedError('%s implements the inference (sampling) path only; wrap calls in torch.no_grad() / '
+                                      'model.eval() (training is out of scope, SURVEY.md §8(f).4)' % type(self).__name__)
         eng = self.engine(xh.device)
         plan = self.plan_for(node_mask)
         ctx_emb = self.context_embedding(context)
         return eng.denoise(plan, xh, edge_x, noise_level, ctx_emb, cond_x, cond_edge_x)
 
 
+def _check_supported(config, who):
+    m, d = config.model, config.data
+    in_node_dim = d.atom_types + int(m.include_fc_charge)
+    supported = (in_node_dim == 6 and m.nf == 256 and m.n_layers == 8 and m.n_heads == 16 and
+                 m.n_extra_heads == 2 and m.mlp_ratio == 2 and m.edge_ch == 2 and m.dist_gbf and m.cond_time and
+                 m.pred_data and m.CoM and m.softmax_inf and m.gbf_name == 'CondGaussianLayer' and
+                 float(m.spatial_cut_off) == 2.0 and float(m.edge_quan_th) == 0.0 and
+                 list(m.patch_len) == [20, 50, 50] and list(m.stride) == [10, 25, 25])
+    if not supported:
+        raise ValueError('%s kernels are specialised for the QM9S DiffSpectra configuration '
+                         '(configs/diffspectra_qm9s.py:44-76); got a different model config' % who)
+
+
+class DMT_B200(_B200Denoiser):
+    """Conditional Diffusion Molecule Transformer with self-conditioning, B200-native forward."""
+    MODEL_KIND = 'DMT'
+
+    def __init__(self, config):
+        super().__init__()
+        m, d = config.model, config.data
+        in_node_dim = d.atom_types + int(m.include_fc_charge)
+        hidden_dim = m.nf
+        edge_hidden_dim = m.nf // 4
+        n_layers = m.n_layers
+        time_dim = hidden_dim * 4
+        _check_supported(config, 'DMT_B200')
+        self.n_layers = n_layers
+
+        self.node_emb = nn.Linear(in_node_dim * 2, hidden_dim)
+        self.edge_emb = nn.Linear(m.edge_ch * 2 + edge_hidden_dim, edge_hidden_dim)
+        self.dist_layer = _CondGaussianParams(edge_hidden_dim, time_dim)
+        cat_node_dim = (hidden_dim * 2) // n_layers
+        cat_edge_dim = (edge_hidden_dim * 2) // n_layers
+        for i in range(n_layers):
+            self.add_module('e_block_%d' % i, _BlockParams(hidden_dim, edge_hidden_dim, time_dim, m.n_extra_heads,
+                                                           m.n_heads, m.mlp_ratio))
+            self.add_module('node_%d' % i, nn.Linear(hidden_dim, cat_node_dim))
+            self.add_module('edge_%d' % i, nn.Linear(edge_hidden_dim, cat_edge_dim))
+        self.node_pred_mlp = _mlp3(cat_node_dim * n_layers + hidden_dim, hidden_dim, hidden_dim // 2, in_node_dim)
+        self.edge_type_mlp = _mlp3(cat_edge_dim * n_layers + edge_hidden_dim, edge_hidden_dim, edge_hidden_dim // 2,
+                                   m.edge_ch - 1)
+        self.edge_exist_mlp = _mlp3(cat_edge_dim * n_layers + edge_hidden_dim, edge_hidden_dim, edge_hidden_dim // 2, 1)
+        self.time_mlp = nn.Sequential(_SinEmbParams(16), nn.Linear(17, time_dim), nn.GELU(), nn.Linear(time_dim, time_dim))
+        self.cond_encoder = _SpecFormerParams(m.patch_len, m.stride, hidden_dim, d.spectra_version)
+        self.cond_lin = nn.Linear(hidden_dim, time_dim)
+        self._init_plumbing(config)
+
+
+class _NodeEmbedParams(nn.Module):             # models/dmt_wo_eq.py:629-637
+    def __init__(self, in_node_features, hidden_size):
+        super().__init__()
+        self.x_linear = nn.Linear(in_node_features, hidden_size * 2)
+        self.pos_linear = nn.Linear(3, hidden_size * 2)
+        self.mlp = nn.Sequential(nn.GELU(), nn.Linear(hidden_size * 2, hidden_size))
+
+
+class _TransOptimV2Params(nn.Module):          # models/dmt_wo_eq.py:175-206
+    def __init__(self, x_channels, out_channels, heads, edge_dim):
+        super().__init__()
+        self.lin_qkv = nn.Linear(x_channels, heads * out_channels * 3)
+        self.lin_kv_e = nn.Linear(edge_dim, heads * out_channels * 2, bias=False)
+        self.proj = nn.Linear(heads * out_channels, heads * out_channels)
+
+
+class _WoBlockParams(nn.Module):               # models/dmt_wo_eq.py:389-472 (pair_update=True, cond_time=True, trans_ver='v2')
+    def __init__(self, node_dim, edge_dim, time_dim, heads, mlp_ratio):
+        super().__init__()
+        self.attn_mpnn = _TransOptimV2Params(node_dim, node_dim // heads, heads, edge_dim)
+        self.ff_linear1 = nn.Linear(node_dim, node_dim * mlp_ratio)
+        self.ff_linear2 = nn.Linear(node_dim * mlp_ratio, node_dim)
+        self.node2edge_lin = nn.Linear(node_dim * 2, edge_dim)
+        self.ff_linear3 = nn.Linear(edge_dim, edge_dim * mlp_ratio)
+        self.ff_linear4 = nn.Linear(edge_dim * mlp_ratio, edge_dim)
+        self.node_time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_dim, node_dim * 6))
+        self.edge_time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_dim, edge_dim * 6))
+
+
+class DMT_WO_EQ_B200(_B200Denoiser):
+    """Non-equivariant ablation (reference: models/dmt_wo_eq.py:646-937, registry name 'DMT_WO_EQ'), B200-native
+    forward.  Same parameter names / shapes / registration order as the reference class."""
+    MODEL_KIND = 'DMT_WO_EQ'
+
+    def __init__(self, config):
+        super().__init__()
+        m, d = config.model, config.data
+        _check_supported(config, 'DMT_WO_EQ_B200')
+        if _cfg(m, 'trans_ver', 'v2') == 'v1':
+            raise ValueError("DMT_WO_EQ_B200 implements trans_ver='v2' (TransLayerOptimV2), the reference default")
+        in_node_dim = d.atom_types + int(m.include_fc_charge)
+        hidden_dim, edge_hidden_dim, n_layers = m.nf, m.nf // 4, m.n_layers
+        time_dim = hidden_dim * 4
+        self.n_layers = n_layers
+        self.node_emb = _NodeEmbedParams(in_node_dim * 2, hidden_dim)
+        self.edge_emb = nn.Linear(m.edge_ch * 2 + edge_hidden_dim, edge_hidden_dim)
+        self.dist_layer = _CondGaussianParams(edge_hidden_dim, time_dim)
+        cat_node_dim = (hidden_dim * 2) // n_layers
+        cat_edge_dim = (edge_hidden_dim * 2) // n_layers
+        for i in range(n_layers):
+            self.add_module('dmt_block_%d' % i, _WoBlockParams(hidden_dim, edge_hidden_dim, time_dim, m.n_heads, m.mlp_ratio))
+            self.add_module('node_%d' % i, nn.Linear(hidden_dim, cat_node_dim))
+            self.add_module('edge_%d' % i, nn.Linear(edge_hidden_dim, cat_edge_dim))
+        self.node_pred_mlp = _mlp3(cat_node_dim * n_layers + hidden_dim, hidden_dim, hidden_dim // 2, in_node_dim)
+        self.pos_pred_mlp = nn.Sequential(nn.Linear(cat_node_dim * n_layers + hidden_dim, hidden_dim, bias=False), nn.Tanh(),
+                                          nn.Linear(hidden_dim, 3, bias=False))
+        self.edge_type_mlp = _mlp3(cat_edge_dim * n_layers + edge_hidden_dim, edge_hidden_dim, edge_hidden_dim // 2,
+                                   m.edge_ch - 1)
+        self.edge_exist_mlp = _mlp3(cat_edge_dim * n_layers + edge_hidden_dim, edge_hidden_dim, edge_hidden_dim // 2, 1)
+        self.time_mlp = nn.Sequential(_SinEmbParams(16), nn.Linear(17, time_dim), nn.GELU(), nn.Linear(time_dim, time_dim))
+        self.cond_encoder = _SpecFormerParams(m.patch_len, m.stride, hidden_dim, d.spectra_version)
+        self.cond_lin = nn.Linear(hidden_dim, time_dim)
+        self._init_plumbing(config)
+
+
 def register(models_utils=None):
-    """Register DMT_B200 in the reference's model registry (models/utils.py:5-21) so that
-    `main.py --mode eval --config.model.name DMT_B200` builds it through create_model()."""
+    """Register DMT_B200 / DMT_WO_EQ_B200 in the reference's model registry (models/utils.py:5-21) so that
+    `main.py --mode eval --config.model.name DMT_B200` builds them through create_model()."""
     if models_utils is None:
         import models.utils as models_utils          # the reference package, when it is on sys.path
-    if 'DMT_B200' not in models_utils._MODELS:
-        models_utils.register_model(DMT_B200, name='DMT_B200')
+    for cls in (DMT_B200, DMT_WO_EQ_B200):
+        if cls.__name__ not in models_utils._MODELS:
+            models_utils.register_model(cls, name=cls.__name__)
     return DMT_B200

@@ -38,6 +38,9 @@ extern "C" {
 #define DS_SPECTRA_RAMAN 2
 #define DS_SPECTRA_ALL 3
 
+#define DS_MODEL_DMT 0       /* models/dmt.py DMT (equivariant) */
+#define DS_MODEL_DMT_WO_EQ 1 /* models/dmt_wo_eq.py DMT_WO_EQ (non-equivariant ablation) */
+
 typedef struct ds_ctx ds_ctx;
 
 const char* ds_last_error(void);
@@ -46,6 +49,8 @@ int ds_version(void);
 /* Context = one model instance on one device.  Replaces models/utils.py:24-28 (create_model -> .to(device));
  * one context per process/GPU instead of nn.DataParallel replication. */
 int ds_create(ds_ctx** out, int device, int mode, int spectra_version);
+/* Same with the model family selected explicitly (registry names 'DMT' / 'DMT_WO_EQ', models/utils.py:5-21). */
+int ds_create_model(ds_ctx** out, int device, int mode, int spectra_version, int model_kind);
 int ds_destroy(ds_ctx* ctx);
 /* kernels launched (or replayed from the captured step graph) through this context so far */
 long long ds_launch_count(ds_ctx* ctx);

@@ -13,6 +13,7 @@ pinned against outputs of the UNMODIFIED reference modules run in the build cont
 
 Reference lines followed (relative to /root/reference):
   denoiser       models/dmt.py:306-413 (DMT.forward), :122-174 (EquivariantMixBlock), :37-60 (MultiCondEquiUpdate)
+  ablation       models/dmt_wo_eq.py:811-937 (DMT_WO_EQ.forward), :486-626 (block), :207-259 (attention), :629-643 (NodeEmbed)
   attention      models/layers.py:131-186 (TransMixLayer) + PyG MessagePassing/softmax semantics
   RBF            models/layers.py:291-295, 328-334 ; CoorsNorm :337-347 ; sinusoidal emb :283-288
   masks / noise  models/utils.py:38-45, 67-106, 118-144
@@ -254,6 +255,96 @@ def dmt_forward(sd, xh, node_mask, edge_mask, edge_x, noise_level, cond_x=None, 
     if return_intermediates:
         return out, edge_final, inter
     return out, edge_final
+
+
+# ----------------------------------------------------------------------------- DMT_WO_EQ (non-equivariant ablation)
+def dmt_wo_eq_forward(sd, xh, node_mask, edge_mask, edge_x, noise_level, cond_x=None, cond_edge_x=None,
+                      ctx_emb=None, n_layers=8, n_heads=16):
+    """Dense restatement of DMT_WO_EQ.forward (models/dmt_wo_eq.py:811-937) with DMT_WO_EQ_Block (:486-626),
+    TransLayerOptimV2 (:207-259) and NodeEmbed (:629-643).  Edge tensors are indexed [b, r, c] for the reference's
+    sparse edge (r = edge_index[0] = source, c = edge_index[1] = target); they are NOT symmetric after the first
+    block (node2edge_lin acts on cat[h_r, h_c]).  Returns ([B,N,9], [B,N,N,2])."""
+    B, N, _ = xh.shape
+    dt = xh.dtype
+    A = edge_mask.reshape(B, N, N).to(dt)
+    nm = node_mask.reshape(B, N, 1).to(dt)
+    pos_init = xh[:, :, 0:3]
+    h = xh[:, :, 3:]
+    if cond_x is None:
+        cond_x = torch.zeros_like(xh)
+        cond_edge_x = torch.zeros_like(edge_x)
+    cond_pos = cond_x[:, :, 0:3]
+    feat = torch.cat([h, cond_x[:, :, 3:]], dim=-1)
+    # NodeEmbed (:638-643)
+    h = _lin(sd, 'node_emb.mlp.1', F.gelu(_lin(sd, 'node_emb.x_linear', feat) + _lin(sd, 'node_emb.pos_linear', pos_init)))
+
+    temb = time_embedding(sd, noise_level) + ctx_emb
+    temb_e = temb[:, None, None, :]
+    s_act = F.silu(temb)
+
+    d = cond_pos[:, :, None, :] - cond_pos[:, None, :, :]
+    r0 = (d ** 2).sum(-1, keepdim=True)
+    if float((r0[..., 0] * A).sum()) == 0:                       # batch-global shortcut (:890-891)
+        d0 = r0.repeat(1, 1, 1, 64)
+    else:
+        d0 = _cond_rbf(sd, 'dist_layer', r0, temb_e)
+    e = _lin(sd, 'edge_emb', torch.cat([edge_x, cond_edge_x, d0], dim=-1))      # [B,r,c,64]
+
+    H, C = n_heads, 16
+    Am = A[..., None]
+    atom_hids, edge_hids = [h], [e]
+    for l in range(n_layers):
+        bp = 'dmt_block_%d.' % l
+        h_in, e_in = h, e
+        nsm = F.linear(s_act, sd[bp + 'node_time_mlp.1.weight'], sd[bp + 'node_time_mlp.1.bias'])
+        esm = F.linear(s_act, sd[bp + 'edge_time_mlp.1.weight'], sd[bp + 'edge_time_mlp.1.bias'])
+        nsh1, nsc1, ng1, nsh2, nsc2, ng2 = [t[:, None, :] for t in nsm.chunk(6, dim=1)]
+        esh1, esc1, eg1, esh2, esc2, eg2 = [t[:, None, None, :] for t in esm.chunk(6, dim=1)]
+        hh = _mod(_ln(h), nsh1, nsc1)
+        ea = _mod(_ln(e), esh1, esc1)
+        # TransLayerOptimV2: query of the TARGET c, key / value of the SOURCE r plus the edge terms of (r -> c)
+        ap = bp + 'attn_mpnn.'
+        qkv = _lin(sd, ap + 'lin_qkv', hh).view(B, N, H, 3, C)
+        q, k, v = qkv.unbind(dim=3)
+        ekv = F.linear(ea, sd[ap + 'lin_kv_e.weight']).view(B, N, N, H, 2, C)
+        ek, ev = ekv.unbind(dim=4)
+        kk = k[:, :, None, :, :] + ek                                           # [B,r,c,H,C]
+        vv = v[:, :, None, :, :] + ev
+        alpha = torch.einsum('bchd,brchd->brch', q, kk) / math.sqrt(C)
+        lmask = torch.where(Am > 0, alpha, torch.full_like(alpha, float('-inf')))
+        mx = lmask.max(dim=1, keepdim=True).values
+        mx = torch.where(torch.isfinite(mx), mx, torch.zeros_like(mx))
+        ex = torch.exp(lmask - mx) * Am
+        att = ex / (ex.sum(dim=1, keepdim=True) + 1e-16)
+        hn = torch.einsum('brch,brchd->bchd', att, vv).reshape(B, N, H * C)
+        hn = _lin(sd, ap + 'proj', hn)
+        # node update (:587-600): the FFN residual base is the UN-normalised sum
+        h1 = h_in + ng1 * hn
+        h = h1 + ng2 * _lin(sd, bp + 'ff_linear2', F.gelu(_lin(sd, bp + 'ff_linear1', _mod(_ln(h1), nsh2, nsc2))))
+        # edge update (:603-626): node2edge_lin(cat[hn_r, hn_c])
+        he = _lin(sd, bp + 'node2edge_lin', torch.cat([hn[:, :, None, :].expand(B, N, N, H * C),
+                                                      hn[:, None, :, :].expand(B, N, N, H * C)], dim=-1))
+        e1 = e_in + eg1 * he
+        e = e1 + eg2 * _lin(sd, bp + 'ff_linear4', F.gelu(_lin(sd, bp + 'ff_linear3', _mod(_ln(e1), esh2, esc2))))
+        atom_hids.append(_lin(sd, 'node_%d' % l, h))
+        edge_hids.append(_lin(sd, 'edge_%d' % l, e))
+
+    ah = torch.cat(atom_hids, dim=-1)
+    eh = torch.cat(edge_hids, dim=-1)
+
+    def mlp3(name, x):
+        x = F.silu(_lin(sd, name + '.0', x))
+        x = F.silu(_lin(sd, name + '.2', x))
+        return _lin(sd, name + '.4', x)
+
+    atom_pred = mlp3('node_pred_mlp', ah) * nm
+    edge_pred = torch.cat([mlp3('edge_exist_mlp', eh), mlp3('edge_type_mlp', eh)], dim=-1) * Am
+    edge_final = 0.5 * (edge_pred + edge_pred.permute(0, 2, 1, 3))
+    pos = F.linear(torch.tanh(F.linear(ah, sd['pos_pred_mlp.0.weight'])), sd['pos_pred_mlp.2.weight']) * nm
+    if bool(torch.isnan(pos).any()):
+        pos = torch.zeros_like(pos)
+    pos = pos - pos.sum(dim=1, keepdim=True) / nm.sum(1, keepdim=True) * nm
+    return torch.cat([pos, atom_pred], dim=2), edge_final
 
 
 # ----------------------------------------------------------------------------- schedule + sampler

@@ -18,9 +18,9 @@ from .ref_harness import load_reference
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
 
 
-def _model(R, version, salt=0, coord_scale=None):
+def _model(R, version, salt=0, coord_scale=None, cls='DMT'):
     R.config.data.spectra_version = version
-    m = R.DMT(R.config).eval()
+    m = getattr(R, cls)(R.config).eval()
     sd = m.state_dict()
     W.keyed_fill_(sd, salt=salt, coord_scale=coord_scale)
     m.load_state_dict(sd)
@@ -100,6 +100,41 @@ def gen_denoiser(R):
                    os.path.join(OUT, 'denoiser_%s.pt' % version))
 
 
+def gen_denoiser_wo_eq(R):
+    """DMT_WO_EQ (models/dmt_wo_eq.py): teacher-forced calls at step 0 and a self-conditioned step, plus a 10-step
+    free-running trajectory with the reference sampler, allspectra."""
+    from . import dense_oracle as O
+    version, salt = 'allspectra', 3
+    m = _model(R, version, salt=salt, cls='DMT_WO_EQ')
+    n = torch.tensor([29, 9, 17, 2, 23])
+    B, N = len(n), 29
+    nm, em = W.make_masks(n, N)
+    ctx = W.synthetic_spectra(B, version, seed=91)
+    g = torch.Generator().manual_seed(300)
+    x = O.node_noise_from_raw(torch.randn(B, N, 3, generator=g), torch.randn(B, N, 6, generator=g), nm)
+    ex = _sym_edge(B, N, 2, em, g)
+    cases = {}
+    with torch.no_grad():
+        nl0 = torch.full((B,), -9.5)
+        p0, e0 = m(nl0, x, nm, em, edge_x=ex, noise_level=nl0, cond_x=None, cond_edge_x=None, context=ctx)
+        cases['step0'] = dict(x=x, edge_x=ex, noise_level=nl0, cond_x=None, cond_edge_x=None, pred=p0, edge_pred=e0)
+        x1, ex1 = 0.9 * x + 0.1 * p0, 0.9 * ex + 0.1 * e0
+        nl1 = torch.linspace(-3., 4., B)
+        p1, e1 = m(nl1, x1, nm, em, edge_x=ex1, noise_level=nl1, cond_x=p0, cond_edge_x=e0, context=ctx)
+        cases['selfcond'] = dict(x=x1, edge_x=ex1, noise_level=nl1, cond_x=p0, cond_edge_x=e0, pred=p1, edge_pred=e1)
+        ns = R.NoiseScheduleVP('cosine', continuous_beta_0=0.1, continuous_beta_1=20.)
+        steps = 10
+        sampler = R.AncestralSampler(ns, torch.linspace(ns.T, 1e-3, steps), True, True, True,
+                                     R.get_self_cond_fn(R.config), sampling_temperature=1.0)
+        torch.manual_seed(43)
+        z = R.mutils.sample_combined_position_feature_noise(B, N, 6, nm)
+        ez = R.mutils.sample_symmetric_edge_feature_noise(B, N, 2, em)
+        x_mean, ex_mean = sampler.sampling(m, z, nm, em, ez, ctx)
+    torch.save(dict(version=version, salt=salt, coord_scale=None, n_atoms=n, N=N, ctx_seed=91, cases=cases,
+                    traj=dict(steps=steps, seed=43, x_mean=x_mean, edge_x_mean=ex_mean)),
+               os.path.join(OUT, 'denoiser_wo_eq_allspectra.pt'))
+
+
 def gen_sampler(R):
     """Free-running ancestral sampling with the reference AncestralSampler + post_process."""
     from . import dense_oracle as O
@@ -144,6 +179,7 @@ def main():
     gen_schedule(R)
     gen_noise_kat(R)
     gen_denoiser(R)
+    gen_denoiser_wo_eq(R)
     gen_sampler(R)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -13,12 +13,13 @@ from tests.helpers import GOLDEN
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize('kind', ['DMT', 'DMT_WO_EQ'])
 @pytest.mark.parametrize('version', ['allspectra', 'ir'])
-def test_parameter_manifest_matches_reference(version):
+def test_parameter_manifest_matches_reference(version, kind):
     from diffspectra_b200.config import get_config
-    from diffspectra_b200.model import DMT_B200
-    man = json.load(open(os.path.join(GOLDEN, 'param_manifest.json')))[version]
-    m = DMT_B200(get_config(version, device='cpu'))
+    from diffspectra_b200.model import DMT_B200, DMT_WO_EQ_B200
+    man = json.load(open(os.path.join(GOLDEN, 'param_manifest.json')))[version if kind == 'DMT' else 'wo_eq_' + version]
+    m = (DMT_B200 if kind == 'DMT' else DMT_WO_EQ_B200)(get_config(version, device='cpu'))
     assert [[n, list(p.shape)] for n, p in m.named_parameters()] == man['params']
     assert [[n, list(b.shape)] for n, b in m.named_buffers()] == man['buffers']
     # strict load of a DataParallel-style ('module.'-prefixed) checkpoint works on the wrapped module (utils.py:15-19)

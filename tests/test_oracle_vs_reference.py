@@ -34,6 +34,30 @@ def test_oracle_matches_live_reference_ir():
     assert rel_l2(q, p) < 3e-6 and rel_l2(f, e) < 3e-6
 
 
+@pytest.mark.parametrize('with_cond', [True, False])
+def test_oracle_matches_live_reference_dmt_wo_eq(with_cond):
+    R = load_reference()
+    R.config.data.spectra_version = 'ir'
+    m = R.DMT_WO_EQ(R.config).eval()
+    sd = m.state_dict()
+    W.keyed_fill_(sd, salt=7)
+    m.load_state_dict(sd)
+    n = torch.tensor([2, 19, 8, 1])
+    B, N = 4, 19
+    nm, em = W.make_masks(n, N)
+    ctx = W.synthetic_spectra(B, 'ir', seed=3)
+    g = torch.Generator().manual_seed(1)
+    x = O.node_noise_from_raw(torch.randn(B, N, 3, generator=g), torch.randn(B, N, 6, generator=g), nm)
+    ex = O.edge_noise_from_raw(torch.randn(B, 2, N, N, generator=g), em)
+    cx = O.node_noise_from_raw(torch.randn(B, N, 3, generator=g), torch.randn(B, N, 6, generator=g), nm) if with_cond else None
+    cex = O.edge_noise_from_raw(torch.randn(B, 2, N, N, generator=g), em) if with_cond else None
+    nl = torch.tensor([-4., 0.5, 7., 2.])
+    with torch.no_grad():
+        p, e = m(nl, x, nm, em, edge_x=ex, noise_level=nl, cond_x=cx, cond_edge_x=cex, context=ctx)
+        q, f = O.dmt_wo_eq_forward(sd, x, nm, em, ex, nl, cx, cex, O.context_embedding(sd, ctx, 'ir'))
+    assert rel_l2(q, p) < 3e-6 and rel_l2(f, e) < 3e-6
+
+
 def test_our_schedule_class_matches_reference_class():
     R = load_reference()
     from diffspectra_b200.noise_schedule import NoiseScheduleVP, ancestral_coefficients
