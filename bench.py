@@ -28,12 +28,22 @@ if ROOT not in sys.path:
 METRIC = 'molecules/sec (QM9S allspectra, 1000 steps)'
 UNIT = 'molecules/s'
 VERSION = 'allspectra'
-N_PAD = 29
 
 
-def alg_flops(n):
-    """ALGORITHMIC FLOPs of one molecule x one denoiser step with n atoms."""
-    return 2 * (21007360 + 5197568 * n + 1290560 * n * (n - 1))
+def alg_flops(n, model='DMT'):
+    """ALGORITHMIC FLOPs of one molecule x one denoiser step with n atoms: adaLN hoisted
+    per molecule, node parts of edge Linears hoisted per atom, directed edges, no credit for redundant reference work
+    and no deduction for exploiting symmetry."""
+    if model == 'DMT':
+        return 2 * (21007360 + 5197568 * n + 1290560 * n * (n - 1))
+    # DMT_WO_EQ (models/dmt_wo_eq.py): per molecule: time MLP + 8 x (1536 + 384) adaLN rows + root RBF rows
+    m_mol = 17 * 1024 + 1024 * 1024 + 8 * (1536 + 384) * 1024 + 2 * 1024
+    # per atom: NodeEmbed, 8 x (qkv, proj, hoisted node2edge halves, FFN, skip), atom head, position head
+    m_node = (15 * 512 + 512 * 256) + 8 * (256 * 768 + 256 * 256 + 2 * 256 * 64 + 2 * 256 * 512 + 256 * 64) + \
+             (768 * 256 + 256 * 128 + 128 * 6) + (768 * 256 + 256 * 3)
+    # per directed edge: root embedding, 8 x (lin_kv_e, q.(k+ek) and alpha (v+ev), FFN, skip), two edge heads
+    m_edge = 68 * 64 + 8 * (64 * 512 + 2 * 256 + 2 * 64 * 128 + 64 * 16) + 2 * (192 * 64 + 64 * 32 + 32)
+    return 2 * (m_mol + m_node * n + m_edge * n * (n - 1))
 
 
 def load_peaks():
@@ -80,18 +90,22 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- the reference arm / CPU baseline
-def cpu_reference_rate(sample_b=16, sample_steps=4, repeats=1):
+def cpu_reference_rate(sample_b=16, sample_steps=4, repeats=1, model='DMT', n_pad=29, all_max=False):
     """Oracle port of the reference PyTorch path (dense restatement, oracle/dense_oracle.py) on the host cores,
     allspectra, on `sample_b` molecules x `sample_steps` denoiser steps (+ one SpecFormer pass per step, as the
     reference recomputes it every call), extrapolated to 1000 steps.  Returns (molecules/s, seconds, description)."""
     import torch
     from diffspectra_b200.config import get_config
-    from diffspectra_b200.model import DMT_B200
+    from diffspectra_b200.model import DMT_B200, DMT_WO_EQ_B200
     from oracle import dense_oracle as O
     from oracle import weights as W
+    N_PAD = n_pad
     torch.manual_seed(42)
-    sd = DMT_B200(get_config(VERSION, device='cpu')).state_dict()
-    n = W.sample_n_atoms(sample_b, seed=1234)
+    sd = (DMT_B200 if model == 'DMT' else DMT_WO_EQ_B200)(get_config(VERSION, device='cpu')).state_dict()
+    fwd = O.dmt_forward if model == 'DMT' else O.dmt_wo_eq_forward
+    n = W.sample_n_atoms(sample_b, seed=1234, max_n=min(n_pad, 29))
+    if all_max:
+        n[:] = n_pad
     nm, em = W.make_masks(n, N_PAD)
     ctx = W.synthetic_spectra(sample_b, VERSION, seed=1235)
     table = O.schedule_table(1000)[:: max(1, 1000 // sample_steps)][:sample_steps]
@@ -101,7 +115,7 @@ def cpu_reference_rate(sample_b=16, sample_steps=4, repeats=1):
     raw = [O.draw_step_noise(sample_b, N_PAD, nm, em, generator=g) for _ in range(sample_steps)]
 
     def denoise(x, ex, nl, cx, cex):          # the reference re-runs SpecFormer inside every call (dmt.py:348-350)
-        return O.dmt_forward(sd, x, nm, em, ex, nl, cx, cex, O.context_embedding(sd, ctx, VERSION))
+        return fwd(sd, x, nm, em, ex, nl, cx, cex, O.context_embedding(sd, ctx, VERSION))
 
     best = None
     with torch.no_grad():
@@ -112,9 +126,9 @@ def cpu_reference_rate(sample_b=16, sample_steps=4, repeats=1):
             best = dt if best is None else min(best, dt)
     per_step = best / sample_steps
     rate = sample_b / (per_step * 1000.0)
-    desc = ('oracle port of the reference PyTorch path, allspectra, B=%d molecules (QM9S histogram, N_pad=29) x %d of 1000 '
+    desc = ('oracle port of the reference PyTorch path (%s), allspectra, B=%d molecules (%s, N_pad=%d) x %d of 1000 '
             'denoiser steps (SpecFormer recomputed each step like the reference), %.2f s/step, extrapolated to 1000 steps'
-            % (sample_b, sample_steps, per_step))
+            % (model, sample_b, 'all n=%d' % n_pad if all_max else 'QM9S histogram', n_pad, sample_steps, per_step))
     return rate, best, desc
 
 
@@ -125,11 +139,11 @@ def run_reference(args):
         return
     cores = torch.get_num_threads()
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_rate(8, 1)
+        cpu_reference_rate(8, 1, model=args.model, n_pad=args.n_pad, all_max=args.all_max)
     rates, secs = [], 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r, s, desc = cpu_reference_rate(16, 2)
+        r, s, desc = cpu_reference_rate(16, 2, model=args.model, n_pad=args.n_pad, all_max=args.all_max)
         rates.append(r)
         secs += s
         if time.perf_counter() - t0 > 150:
@@ -137,10 +151,9 @@ def run_reference(args):
     value = len(rates) * 16 / sum(16 / r for r in rates)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(rates),
-        'warmup': min(args.warmup, 1), 'ms_per_step': 1000.0 * 1024 / value, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': min(args.warmup, 1), 'ms_per_step': 1000.0 * args.batch / value, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'DMT allspectra sampling, 1000 steps, batch 1024 (BASELINE.json configs[1]); bounded sample',
-                   'batch': 1024, 'diffusion_steps': 1000},
+        'config': {'workload': workload_name(args) + '; bounded sample', 'batch': args.batch, 'diffusion_steps': 1000},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -156,7 +169,7 @@ def run_ours(args):
     from diffspectra_b200 import build as B
     from diffspectra_b200.config import get_config
     from diffspectra_b200.distributed import gather_records, pack_records
-    from diffspectra_b200.model import DMT_B200
+    from diffspectra_b200.model import DMT_B200, DMT_WO_EQ_B200
     from diffspectra_b200.noise_schedule import NoiseScheduleVP, ancestral_coefficients
     from oracle import weights as W          # synthetic inputs only (atom-count histogram, spectra)
 
@@ -172,12 +185,13 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
-    Bsz, S = args.batch, args.diffusion_steps
+    Bsz, S, N_PAD = args.batch, args.diffusion_steps, args.n_pad
     torch.manual_seed(42)                                   # random-init weights of the reference architecture
-    model = DMT_B200(get_config(VERSION, device=str(dev), precision=args.precision)).eval().to(dev)
+    cls = DMT_B200 if args.model == 'DMT' else DMT_WO_EQ_B200
+    model = cls(get_config(VERSION, device=str(dev), precision=args.precision)).eval().to(dev)
     eng = model.engine(dev)
-    n_atoms = W.sample_n_atoms(Bsz, seed=1234 + rank).numpy().astype(np.int32)
-    if args.all29:
+    n_atoms = W.sample_n_atoms(Bsz, seed=1234 + rank, max_n=min(N_PAD, 29)).numpy().astype(np.int32)
+    if args.all_max:
         n_atoms[:] = N_PAD
     plan = eng.plan(n_atoms, N_PAD)
     spectra_host = [t.pin_memory() for t in W.synthetic_spectra(Bsz, VERSION, seed=1235 + rank)]
@@ -230,7 +244,7 @@ def run_ours(args):
         clk = clocks.stop() if rank == 0 else None
         one_round(0, True)
         ms_e2e, _ = timed(args.steps, True, args.warmup + args.steps)
-        kern = kernel_rooflines(eng, dev) if rank == 0 else None
+        kern = step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args) if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -240,17 +254,19 @@ def run_ours(args):
     mols = Bsz * world * args.steps
     value = mols / (ms / 1000.0)
     e2e_value = mols / (ms_e2e / 1000.0)
-    flops_round = float(sum(alg_flops(int(n)) for n in n_atoms)) * S            # rank 0's shard, denoiser only
+    flops_round = float(sum(alg_flops(int(n), args.model) for n in n_atoms)) * S            # rank 0's shard, denoiser only
     achieved = flops_round * args.steps / (ms / 1000.0) / 1e12                  # TFLOP/s per GPU
     h2d = sum(t.numel() * 4 for t in spectra_host) + n_atoms.nbytes
     d2h = int(rec_host.numel() * rec_host.element_size()) if rec_host is not None else 0
-    cpu_rate, cpu_s, cpu_desc = cpu_reference_rate(16, 2) if args.cpu_baseline else (None, 0, 'skipped (--no-cpu-baseline)')
+    cpu_rate, cpu_s, cpu_desc = (cpu_reference_rate(16, 2, model=args.model, n_pad=N_PAD, all_max=args.all_max)
+                                 if args.cpu_baseline else (None, 0, 'skipped (--no-cpu-baseline)'))
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': 'DMT allspectra sampling, %d steps, batch %d per GPU (BASELINE.json configs[1])' % (S, Bsz),
-                   'batch_per_gpu': Bsz, 'diffusion_steps': S, 'n_atoms': 'all 29' if args.all29 else 'QM9S histogram, mean %.2f' % n_atoms.mean(),
+        'config': {'workload': workload_name(args), 'model': args.model + '_B200',
+                   'batch_per_gpu': Bsz, 'diffusion_steps': S, 'n_pad': N_PAD,
+                   'n_atoms': 'all %d' % N_PAD if args.all_max else 'QM9S histogram, mean %.2f' % n_atoms.mean(),
                    'noise': 'device Philox', 'l2': 'inputs_exceed_l2 (per-step working set >> 126 MB)',
                    'parallelism': 'dp%d independent shards + 1 all-gather/round' % world},
         'denoiser_steps_per_s': args.steps * S / (ms / 1000.0),
@@ -259,11 +275,11 @@ def run_ours(args):
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'clocks': clk,
-        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
-                     'frac': achieved / peaks['sustained'], 'traffic': None,
-                     'what': 'whole denoiser step: algorithmic FLOPs 2*(21007360+5197568 n+1290560 n(n-1)) per molecule-step '
-                             '(SURVEY.md 8(d)) / CUDA-event time of the timed rounds; peak = sustained bf16, ' + peaks['which'],
-                     'kernels': kern},
+        'roofline': dict(kern['dominant'], step={
+            'bound': 'tensor', 'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['sustained'],
+            'what': 'whole denoiser step: algorithmic FLOPs per molecule-step (SURVEY.md 8(d); bench.alg_flops) / CUDA-event time '
+                    'of the timed rounds; peak = sustained bf16, ' + peaks['which']}, kernels=kern['kernels'],
+            in_stream_step_us=kern['step_us']),
         'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': cpu_desc},
     }
     print(json.dumps(line))
@@ -271,41 +287,103 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def kernel_rooflines(eng, dev):
-    """The dominant kernel timed ALONE with CUDA events: the tcgen05 GEMM on the two largest contraction shapes of a
-    step (coord_mlp.0 over directed edges, lin_edge0|lin_edge1 over pairs), against the burst bf16 peak."""
+def workload_name(args):
+    tag = {29: 'BASELINE.json configs[1]', 64: 'BASELINE.json configs[4] stress shape'}.get(args.n_pad, 'custom shape')
+    if args.model != 'DMT':
+        tag = 'BASELINE.json configs[3]' if args.n_pad == 29 else tag
+    return '%s allspectra sampling, %d steps, batch %d per GPU, N<=%d (%s)' % (args.model, args.diffusion_steps, args.batch,
+                                                                              args.n_pad, tag)
+
+
+def _demangle(name):
+    import re
+    m = re.search(r'\d+(k_[a-z0-9_]+|gemm_tc_kernel|gemm_simt_kernel|coord_fused_kernel)', name)
+    base = m.group(1) if m else name[:40]
+    t = re.search(r'gemm_tc_kernelILi(\d+)ELi(\d+)ELb(\d)E', name)
+    if t:
+        base += '<%s,%s,%s>' % (t.group(1), ('STORE', 'LNMOD', 'RESGATE', 'COORD', 'EHEAD')[int(t.group(2))], t.group(3))
+    return base
+
+
+def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
+    """Every kernel of a denoiser step timed IN STREAM with CUDA events (ds_profile_begin/end around a non-graph
+    ds_sample_loop of 3 steps, warm caches, same inputs as the timed region).  For each kernel: average launch time,
+    ALGORITHMIC bytes / FLOPs per launch and the fraction of the HBM / tensor peak they amount to.
+    The roofline object reports the kernel with the largest share of the step."""
     import ctypes
     import torch
     from diffspectra_b200 import _lib as L
     peaks = load_peaks()
-    res = []
-    for name, M, N, K, act in (('coord_mlp.0 [2Mp,256]x[256,256]+SiLU', 323072, 256, 256, L.ACT_SILU),
-                               ('lin_edge0|1 [Mp,64]x[512,64]+tanh', 161536, 512, 64, L.ACT_TANH),
-                               ('adaLN table [B,1024]x[19584,1024]', 1024, 19584, 1024, L.ACT_NONE)):
-        A = torch.randn(M, K, device=dev).bfloat16()
-        Wt = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
-        bias = torch.zeros(N, device=dev)
-        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-
-        def go():
-            L.check(L.lib().ds_gemm(eng.h, 1, L.ptr(A), K, L.ptr(Wt), K, L.ptr(bias), ctypes.c_void_p(0), 0, L.ptr(out), N,
-                                    M, N, K, L.DT_BF16, L.DT_BF16, act, L.stream_ptr()), 'ds_gemm')
-        for _ in range(3):
-            go()
-        flush = torch.empty(64 << 20, device=dev, dtype=torch.float32)
-        ts = []
-        for _ in range(5):
-            flush.fill_(1.0)                              # L2 flush between timed launches (256 MB > 126 MB L2)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); go(); e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = sorted(ts)[len(ts) // 2]
-        tf = 2.0 * M * N * K / (ms / 1e3) / 1e12
-        gbs = (M * K * 2 + N * K * 2 + M * N * 2) / (ms / 1e3) / 1e9
-        res.append({'kernel': 'gemm_tc_kernel', 'shape': name, 'ms': ms, 'tflops': tf, 'frac_of_burst_bf16': tf / peaks['burst'],
-                    'gbs': gbs, 'frac_of_hbm': gbs / peaks['hbm']})
-    return res
+    lib = L.lib()
+    ctx_emb = eng.context_embedding(spectra_dev)
+    steps = min(3, coef.shape[0])
+    eng.sample_loop(plan, ctx_emb, coef[:steps], None, None, None, seed=1, use_graph=False)      # warm, untimed
+    torch.cuda.synchronize()
+    L.check(lib.ds_profile_begin(), 'ds_profile_begin')
+    eng.sample_loop(plan, ctx_emb, coef[:steps], None, None, None, seed=1, use_graph=False)
+    buf = ctypes.create_string_buffer(1 << 16)
+    L.check(lib.ds_profile_end(buf, ctypes.c_size_t(len(buf))), 'ds_profile_end')
+    Mn, Mp = plan.Mn, plan.Mp
+    Md = 2 * Mp
+    wo = args.model != 'DMT'
+    Me = Md if wo else Mp                       # rows of the edge tensors
+    bytes_of = {      # ALGORITHMIC bytes per launch of the graph-side kernels (what must cross HBM once)
+        'k_attention_grp': Mp * 1024 + Mp + Mn * (1536 + 256 * 6),          # e0|e1 once per pair, flags, q|k|v, hn fp32+bf16
+        'k_wo_attention': Md * 1024 + Mn * (1536 + 512),
+        'k_coord_ln': Mp * 512 + Mn * 1024 + Md * 513,                       # gp, ab in; Z + flags out
+        'k_edge_update1': Mp * (256 + 256 + 128) + Mn * 256,
+        'k_wo_edge_update1': Md * (256 + 256 + 128) + Mn * 512,
+        'k_wo_dir_ln1': Md * (256 + 128),
+        'k_rbf': Mp * 128 + Mn * 12,
+        'k_node_ln1': Mn * (1024 + 512), 'k_node_update1': Mn * (2048 + 1024 + 512), 'k_wo_node_update1': Mn * (2048 + 1024 + 512),
+        'k_pos_update': Md * 4 + Mn * 24,
+        'k_sampler_pairs': Mp * 24, 'k_sampler_nodes': Mn * 108,
+    }
+    rows, total = [], 0.0
+    for line in buf.value.decode().strip().splitlines():
+        name, tag, n, us = line.split('\t')
+        tag, n, us = int(tag), int(n), float(us)
+        total += us
+        kname = _demangle(name)
+        rec = {'kernel': kname, 'launches_per_step': n / steps, 'us_per_launch': us / n, 'us_per_step': us / steps}
+        flops = by = None
+        if tag:
+            mode, N, K, M = (tag >> 61) & 7, (tag >> 46) & 0x7fff, (tag >> 30) & 0xffff, tag & 0x3fffffff
+            rec['shape'] = '[%d,%d]x[%d,%d]' % (M, K, N, K)
+            flops = 2.0 * M * N * K
+            out_b = {0: M * N * 2, 1: M * N * 2, 2: M * N * (4 + 4 + 2), 3: M * 5, 4: M * 8}[mode]
+            by = M * K * 2 + N * K * 2 + out_b
+        else:
+            for key, v in bytes_of.items():
+                if kname.startswith(key):
+                    by = v
+        t = us / n * 1e-6
+        if flops:
+            rec['tflops'] = flops / t / 1e12
+            rec['frac_tensor'] = rec['tflops'] / peaks['burst']
+        if by:
+            rec['alg_bytes'] = int(by)
+            rec['gbs'] = by / t / 1e9
+            rec['frac_hbm'] = rec['gbs'] / peaks['hbm']
+        rows.append(rec)
+    for r in rows:
+        r['share_of_step'] = r['us_per_step'] / (total / steps)
+    rows.sort(key=lambda r: -r['us_per_step'])
+    top = rows[0]
+    tensor_bound = top.get('frac_tensor', 0) > top.get('frac_hbm', 0)
+    dominant = {
+        'kernel': top['kernel'] + (' ' + top['shape'] if 'shape' in top else ''),
+        'bound': 'tensor' if tensor_bound else 'hbm',
+        'achieved': top.get('tflops') if tensor_bound else top.get('gbs'),
+        'peak': peaks['burst'] if tensor_bound else peaks['hbm'],
+        'unit': 'TFLOP/s' if tensor_bound else 'GB/s',
+        'frac': top.get('frac_tensor') if tensor_bound else top.get('frac_hbm'),
+        'traffic': None,
+        'us_per_launch': top['us_per_launch'], 'share_of_step': top['share_of_step'],
+        'what': 'dominant kernel of a denoiser step by in-stream CUDA-event time; achieved = algorithmic bytes (or FLOPs) per '
+                'launch / average launch time; peak = ' + peaks['which'] + ' (burst figures); traffic: see profiles/ for ncu dram bytes',
+    }
+    return {'dominant': dominant, 'kernels': rows[:14], 'step_us': total / steps}
 
 
 def main():
@@ -317,9 +395,13 @@ def main():
     ap.add_argument('--batch', type=int, default=1024)
     ap.add_argument('--diffusion-steps', type=int, default=1000)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--all29', action='store_true', help='worst case: every molecule has 29 atoms')
+    ap.add_argument('--model', default='DMT', choices=['DMT', 'DMT_WO_EQ'])
+    ap.add_argument('--n-pad', type=int, default=29, help='padded atoms per molecule (64 = stress shape, implies --all-max)')
+    ap.add_argument('--all-max', '--all29', dest='all_max', action='store_true', help='worst case: every molecule has n_pad atoms')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
     args = ap.parse_args()
+    if args.n_pad > 29:
+        args.all_max = True            # BASELINE.json configs[4]: synthetic molecules with N atoms each
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -1,5 +1,9 @@
 // C-ABI entry points: context lifetime, error reporting and the GEMM test hook.
 #include <stdarg.h>
+#include <stdio.h>
+
+#include <map>
+#include <vector>
 #include <stdlib.h>
 
 #include "../../include/diffspectra_b200.h"
@@ -17,6 +21,7 @@ void ds_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+DsProf g_ds_prof;
 bool g_ds_use_pdl = false;     // measured on B200: no gain with the implicit trigger (graph replay gaps are already ~0), -3.5% with an early trigger
 
 extern "C" {
@@ -83,6 +88,43 @@ int ds_destroy(ds_ctx* h) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   ds_ctx_free(c);
+  return DS_OK;
+}
+
+int ds_profile_begin(void) {
+  for (auto& r : g_ds_prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_ds_prof.recs.clear();
+  g_ds_prof.on = true;
+  return DS_OK;
+}
+
+int ds_profile_end(char* out, size_t out_bytes) {
+  g_ds_prof.on = false;
+  DS_CUDA_CHECK(cudaDeviceSynchronize());
+  typedef std::pair<const void*, long long> Key;
+  std::map<Key, std::pair<int, double>> agg;
+  std::vector<Key> order;
+  for (auto& r : g_ds_prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) ms = 0.f;
+    const Key k(r.fn, r.tag);
+    auto it = agg.find(k);
+    if (it == agg.end()) { agg[k] = std::make_pair(1, static_cast<double>(ms)); order.push_back(k); }
+    else { it->second.first++; it->second.second += ms; }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_ds_prof.recs.clear();
+  size_t off = 0;
+  if (out && out_bytes) out[0] = 0;
+  for (const Key& k : order) {
+    const char* name = nullptr;
+    if (cudaFuncGetName(&name, k.first) != cudaSuccess || !name) name = "?";
+    const int n = snprintf(out ? out + off : nullptr, out && off < out_bytes ? out_bytes - off : 0, "%s\t%lld\t%d\t%.3f\n", name,
+                           k.second, agg[k].first, agg[k].second * 1000.0);
+    if (n < 0 || !out || off + n >= out_bytes) break;
+    off += n;
+  }
   return DS_OK;
 }
 

@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <vector>
+
 // ----------------------------------------------------------------------------- error codes (mirrored in the header)
 #ifndef DS_OK
 #define DS_OK 0
@@ -54,6 +56,10 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 #else
 __device__ __forceinline__ void pdl_trigger() {}     // implicit trigger at grid completion: only the launch is pre-staged
 #endif
+// In-stream kernel timing (ds_profile_begin / ds_profile_end): every launch is bracketed by two events on its stream.
+struct DsProfRec { const void* fn; long long tag; cudaEvent_t e0, e1; };
+struct DsProf { bool on = false; long long tag = 0; std::vector<DsProfRec> recs; };   // tag: set by the GEMM launcher (shape)
+extern DsProf g_ds_prof;
 extern bool g_ds_use_pdl;      // DS_PDL=1 enables the launch attribute (off by default, see api_core.cu)
 template <typename... KArgs, typename... Args>
 inline cudaError_t ds_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
@@ -67,7 +73,16 @@ inline cudaError_t ds_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_ds_use_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (!g_ds_prof.on) return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  DsProfRec r{reinterpret_cast<const void*>(kernel), g_ds_prof.tag, nullptr, nullptr};
+  g_ds_prof.tag = 0;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, s);
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  cudaEventRecord(r.e1, s);
+  g_ds_prof.recs.push_back(r);
+  return err;
 }
 
 // ----------------------------------------------------------------------------- model dimensions (QM9S config)

@@ -502,6 +502,8 @@ int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
   const int tiles = m_tiles * n_tiles;
   const int sms = (ctx->cta_cap > 0 && ctx->cta_cap < ctx->num_sms) ? ctx->cta_cap : ctx->num_sms;
   const int grid = tiles < sms ? tiles : sms;
+  if (g_ds_prof.on)   // shape tag for ds_profile_end: mode(3) | N(15) | K(16) | M(30)
+    g_ds_prof.tag = (static_cast<long long>(MODE) << 61) | (static_cast<long long>(g.N) << 46) | (static_cast<long long>(g.K) << 30) | g.M;
   ds_launch(gemm_tc_kernel<BN, MODE, TMA_OUT>, dim3(grid), dim3(kThreads), C::kSmemBytes, s, tmA, tmW, tmO, tmR, tmF, ep, g.M, g.N, g.K);
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;

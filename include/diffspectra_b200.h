@@ -55,6 +55,13 @@ int ds_destroy(ds_ctx* ctx);
 /* kernels launched (or replayed from the captured step graph) through this context so far */
 long long ds_launch_count(ds_ctx* ctx);
 
+/* In-stream timing of every kernel launched through the library between the two calls (use ds_sample_loop with
+ * use_graph = 0, or ds_denoise): ds_profile_end synchronises the device and writes one line per kernel,
+ * "<mangled name>\t<tag>\t<launches>\t<total microseconds>\n", into out (tag = mode<<61 | N<<46 | K<<30 | M for the
+ * tcgen05 GEMM, 0 otherwise).  Measurement aid for bench.py; not thread-safe. */
+int ds_profile_begin(void);
+int ds_profile_end(char* out, size_t out_bytes);
+
 /* Weights.  `names[i]` / `ptrs[i]` = state_dict entries (fp32, contiguous, device) of a reference-compatible DMT
  * module, parameters AND BatchNorm buffers, names as in models/dmt.py:211-262 (an optional "module." prefix from
  * nn.DataParallel checkpoints, utils.py:15-19, is stripped).  Re-packs them into `blob` (GEMM-ready bf16/fp32,
