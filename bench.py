@@ -90,11 +90,23 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- the reference arm / CPU baseline
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1: undo that for the CPU arm)."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_reference_rate(sample_b=16, sample_steps=4, repeats=1, model='DMT', n_pad=29, all_max=False):
     """Oracle port of the reference PyTorch path (dense restatement, oracle/dense_oracle.py) on the host cores,
     allspectra, on `sample_b` molecules x `sample_steps` denoiser steps (+ one SpecFormer pass per step, as the
     reference recomputes it every call), extrapolated to 1000 steps.  Returns (molecules/s, seconds, description)."""
     import torch
+    host_threads()
     from diffspectra_b200.config import get_config
     from diffspectra_b200.model import DMT_B200, DMT_WO_EQ_B200
     from oracle import dense_oracle as O
@@ -137,7 +149,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = host_threads()
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_rate(8, 1, model=args.model, n_pad=args.n_pad, all_max=args.all_max)
     rates, secs = [], 0.0
@@ -280,7 +292,7 @@ def run_ours(args):
             'what': 'whole denoiser step: algorithmic FLOPs per molecule-step (SURVEY.md 8(d); bench.alg_flops) / CUDA-event time '
                     'of the timed rounds; peak = sustained bf16, ' + peaks['which']}, kernels=kern['kernels'],
             in_stream_step_us=kern['step_us']),
-        'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': cpu_desc},
+        'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port', 'sample': cpu_desc},
     }
     print(json.dumps(line))
     if world > 1:
