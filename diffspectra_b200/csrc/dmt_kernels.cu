@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, cons
     const AT* ebase = e01 + 256 + lane * 8;
     if constexpr (sizeof(AT) == 2) {
       // four sources per iteration, all eight 16-byte loads issued before the first use; v * e1 as packed bf16
-      // multiplies, weighted accumulation in fp32.  Masked slots (i == j, i >= n) read a valid row with weight 0.
+      // multiplies, weighted accumulation in fp32.  Masked slots (i == j, i >= n) read finite data with weight 0.
       for (int i0 = 0; i0 < n; i0 += 4) {
         uint4 vv[4], ee[4];
         float al[4];
@@ -516,8 +516,10 @@ __global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, cons
           const int row = srow[w][ic];
           const bool ok = (i0 + u < n) && row >= 0;
           al[u] = ok ? slog[w][ic][hh] : 0.f;
-          vv[u] = ldg128_pinned(vbase + static_cast<size_t>(ic) * QKV_LD);
-          ee[u] = ldg128_pinned(ebase + static_cast<size_t>(ok ? row : pbase) * E01_LD);
+          const AT* vr = vbase + static_cast<size_t>(ic) * QKV_LD;
+          vv[u] = ldg128_pinned(vr);
+          // masked slot: any finite, in-bounds data will do (a molecule without pairs owns no e01 row at all)
+          ee[u] = ldg128_pinned(ok ? static_cast<const void*>(ebase + static_cast<size_t>(row) * E01_LD) : static_cast<const void*>(vr));
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {

@@ -41,6 +41,7 @@ def test_fp32_matches_reference_golden(version, case):
     e_edge = rel_l2(epred, c['edge_pred'])
     print(version, case, 'pos %.2e atom %.2e edge %.2e | max %.2e %.2e' % (
         e_pos, e_atom, e_edge, max_abs(pred, c['pred']), max_abs(epred, c['edge_pred'])))
+    assert torch.isfinite(pred).all() and torch.isfinite(epred).all()
     assert e_pos <= FP32_TOL and e_atom <= FP32_TOL and e_edge <= FP32_TOL
     # padded atoms / edges / diagonal are exactly zero, like the reference
     nm, em = W.make_masks(g['n_atoms'], g['N'])
@@ -72,6 +73,7 @@ def test_bf16_matches_reference_golden(version, case):
     e_edge = rel_l2(epred, c['edge_pred'])
     print(version, case, 'bf16 pos %.2e atom %.2e edge %.2e | max %.2e %.2e' % (
         e_pos, e_atom, e_edge, max_abs(pred, c['pred']), max_abs(epred, c['edge_pred'])))
+    assert torch.isfinite(pred).all() and torch.isfinite(epred).all()
     assert e_pos <= BF16_TOL and e_atom <= BF16_TOL and e_edge <= BF16_TOL
 
 

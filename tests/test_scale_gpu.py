@@ -50,6 +50,7 @@ def test_batch_1024_matches_small_batches(precision, tol):
                               cond_x=cx[s].contiguous(), cond_edge_x=cex[s].contiguous())
             e_pos, e_atom, e_edge = rel_l2(full[s][..., :3], sub[..., :3]), rel_l2(full[s][..., 3:], sub[..., 3:]), rel_l2(efull[s], esub)
             print(precision, (lo, hi), 'pos %.2e atom %.2e edge %.2e' % (e_pos, e_atom, e_edge))
+            assert torch.isfinite(sub).all() and torch.isfinite(esub).all()
             assert max(e_pos, e_atom, e_edge) <= tol
     assert torch.isfinite(full).all() and torch.isfinite(efull).all()
     assert (efull - efull.transpose(1, 2)).abs().max() == 0
@@ -71,6 +72,7 @@ def test_stress_shape_n64_matches_oracle(precision, tol):
                                   cex.double(), cemb)
     e_pos, e_atom, e_edge = rel_l2(pred[..., :3], ref[..., :3]), rel_l2(pred[..., 3:], ref[..., 3:]), rel_l2(epred, eref)
     print('N=64', precision, 'pos %.2e atom %.2e edge %.2e' % (e_pos, e_atom, e_edge))
+    assert torch.isfinite(pred).all() and torch.isfinite(epred).all()
     assert max(e_pos, e_atom, e_edge) <= tol
 
 

@@ -34,6 +34,7 @@ def test_wo_eq_matches_reference_golden(case, precision, tol):
                             noise_level=c['noise_level'].cuda(), cond_x=cu(c['cond_x']), cond_edge_x=cu(c['cond_edge_x']))
     e_pos, e_atom, e_edge = rel_l2(pred[..., :3], c['pred'][..., :3]), rel_l2(pred[..., 3:], c['pred'][..., 3:]), rel_l2(epred, c['edge_pred'])
     print('wo_eq', case, precision, 'pos %.2e atom %.2e edge %.2e' % (e_pos, e_atom, e_edge))
+    assert torch.isfinite(pred).all() and torch.isfinite(epred).all()
     assert max(e_pos, e_atom, e_edge) <= tol
     nmc, emc = W.make_masks(n, g['N'])
     assert (pred.cpu() * (1 - nmc)).abs().max() == 0
@@ -90,4 +91,5 @@ def test_wo_eq_n64_and_large_batch():
                                             cex.double(), cemb)
         errs = (rel_l2(pred[..., :3], ref[..., :3]), rel_l2(pred[..., 3:], ref[..., 3:]), rel_l2(epred, eref))
         print('wo_eq N=64', precision, 'pos %.2e atom %.2e edge %.2e' % errs)
+        assert torch.isfinite(pred).all() and torch.isfinite(epred).all()
         assert max(errs) <= tol
