@@ -409,7 +409,7 @@ __device__ __forceinline__ uint4 ldg128_pinned(const void* p) {
 }
 __device__ __forceinline__ float2 ld_pair2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 template <typename AT, bool kFast, int MAXN>
-__global__ void __launch_bounds__(256) k_attention_grp(Plan plan, int ngrp, const AT* __restrict__ qkv,
+__global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, const AT* __restrict__ qkv,
                                                        const AT* __restrict__ e01, const uint8_t* __restrict__ pflags,
                                                        float* __restrict__ hn, AT* __restrict__ hnb) {
   pdl_trigger();
