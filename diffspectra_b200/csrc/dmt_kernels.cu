@@ -9,6 +9,10 @@
 //   * node2edge_lin(h_r + h_c) and the h_row / h_col parts of equi_update.input_lin are applied per atom;
 //   * the four host synchronisations of the reference (nonzero, dense_to_sparse, distances.sum()==0,
 //     isnan) become a precomputed plan and two device-side flags.
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace {
@@ -415,7 +419,10 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
   pdl_trigger();
   pdl_wait();
   __shared__ __align__(16) float sq[ATT_G][256];
-  __shared__ float slog[ATT_G][MAXN][N_HEADS];
+  // logits / softmax weights: fp32 in validation mode; fp16 in production mode (|logit| = O(1), weights in [0,1]) so that
+  // six CTAs leave ~120 KB of the SM's 228 KB to L1, which serves the k / v rows and the second read of every pair row
+  typedef typename std::conditional<kFast, __half, float>::type LT;
+  __shared__ LT slog[ATT_G][MAXN][N_HEADS];
   __shared__ int srow[ATT_G][MAXN];
   const int mol = blockIdx.x / ngrp, j0 = (blockIdx.x % ngrp) * ATT_G;
   const int n = plan.n_atoms[mol];
@@ -470,10 +477,10 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
           a = fmaf(qv.y * kv.y, ev.y, a);
         }
       }
-      slog[jl][i][2 + hh] = a * 0.25f;                 // 1 / sqrt(out_channels = 16)
+      slog[jl][i][2 + hh] = static_cast<LT>(a * 0.25f);   // 1 / sqrt(out_channels = 16)
     } else {
       const int bit = hh - N_SUB;                      // 0: adj2d, 1: adjsp
-      slog[jl][i][bit] = ((pflags[row] >> bit) & 1) ? 1.0f : -1e10f;
+      slog[jl][i][bit] = static_cast<LT>(((pflags[row] >> bit) & 1) ? 1.0f : (kFast ? -60000.0f : -1e10f));   // exp() == 0 either way
     }
   }
   __syncthreads();
@@ -482,15 +489,15 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
     const int jl = t >> 4, hh = t & 15, j = j0 + jl;
     float mx = -INFINITY;
     for (int i = 0; i < n; ++i)
-      if (i != j) mx = fmaxf(mx, slog[jl][i][hh]);
+      if (i != j) mx = fmaxf(mx, static_cast<float>(slog[jl][i][hh]));
     float den = 0.f;
     for (int i = 0; i < n; ++i) {
-      const float ex = (i != j) ? act_exp<kFast>(slog[jl][i][hh] - mx) : 0.f;
-      slog[jl][i][hh] = ex;
+      const float ex = (i != j) ? act_exp<kFast>(static_cast<float>(slog[jl][i][hh]) - mx) : 0.f;
+      slog[jl][i][hh] = static_cast<LT>(ex);
       den += ex;
     }
     const float inv = 1.0f / (den + 1e-16f);
-    for (int i = 0; i < n; ++i) slog[jl][i][hh] *= inv;
+    for (int i = 0; i < n; ++i) slog[jl][i][hh] = static_cast<LT>(static_cast<float>(slog[jl][i][hh]) * inv);
   }
   __syncthreads();
   // pass 2: messages; warp w <-> target j0 + w, lane <-> 8 value channels (one head per 2 lanes):
@@ -515,7 +522,7 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
           const int ic = min(i0 + u, n - 1);
           const int row = srow[w][ic];
           const bool ok = (i0 + u < n) && row >= 0;
-          al[u] = ok ? slog[w][ic][hh] : 0.f;
+          al[u] = ok ? static_cast<float>(slog[w][ic][hh]) : 0.f;
           const AT* vr = vbase + static_cast<size_t>(ic) * QKV_LD;
           vv[u] = ldg128_pinned(vr);
           // masked slot: any finite, in-bounds data will do (a molecule without pairs owns no e01 row at all)
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
 #pragma unroll 4
       for (int i = 0; i < n; ++i) {
         if (i == j) continue;
-        const float al = slog[w][i][hh];
+        const float al = static_cast<float>(slog[w][i][hh]);
         const AT* vr = vbase + static_cast<size_t>(i) * QKV_LD;
         const AT* er = ebase + static_cast<size_t>(srow[w][i]) * E01_LD;
         const float4 v0 = load4<AT>(vr), v1 = load4<AT>(vr + 4);
