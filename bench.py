@@ -317,6 +317,12 @@ def _demangle(name):
     return base
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (MB) from the committed `ncu --set full` capture of this
+# command at batch 1024 / QM9S histogram (profiles/r1_final_ncu.md); reported as roofline.traffic for the same workload only
+NCU_DRAM_MB = {'k_attention_grp': 215.2, 'k_coord_ln': 220.0, 'gemm_tc_kernel<256,COORD,0>': 173.7, 'k_edge_update1': 64.7,
+               'gemm_tc_kernel<64,RESGATE,1>': 101.6, 'gemm_tc_kernel<64,LNMOD,1>': 43.3}
+
+
 def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
     """Every kernel of a denoiser step timed IN STREAM with CUDA events (ds_profile_begin/end around a non-graph
     ds_sample_loop of 3 steps, warm caches, same inputs as the timed region).  For each kernel: average launch time,
@@ -390,10 +396,12 @@ def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
         'peak': peaks['burst'] if tensor_bound else peaks['hbm'],
         'unit': 'TFLOP/s' if tensor_bound else 'GB/s',
         'frac': top.get('frac_tensor') if tensor_bound else top.get('frac_hbm'),
-        'traffic': None,
+        'traffic': (NCU_DRAM_MB.get(top['kernel']) * 1e6 if (args.model == 'DMT' and args.batch == 1024 and args.n_pad == 29 and not args.all_max
+                                                             and top['kernel'] in NCU_DRAM_MB) else None),
         'us_per_launch': top['us_per_launch'], 'share_of_step': top['share_of_step'],
         'what': 'dominant kernel of a denoiser step by in-stream CUDA-event time; achieved = algorithmic bytes (or FLOPs) per '
-                'launch / average launch time; peak = ' + peaks['which'] + ' (burst figures); traffic: see profiles/ for ncu dram bytes',
+                'launch / average launch time; peak = ' + peaks['which'] + ' (burst figures); traffic = ncu dram bytes per launch '
+                '(profiles/r1_final_ncu.md), bytes',
     }
     return {'dominant': dominant, 'kernels': rows[:14], 'step_us': total / steps}
 
