@@ -26,9 +26,9 @@ struct CtxFull : DsContext {
 inline CtxFull* full(ds_ctx* h) { return reinterpret_cast<CtxFull*>(h); }
 
 // plan blob layout (device, int32): n_atoms[B] | noff[B+1] | poff[B+1] | node_info[Mn_max] | pair_info[Mp_max] |
-// dir_info[2*Mp_max] (int4)
+// dir_info[2*Mp_max] (int4) | dir_mol[2*Mp_max] | pair_rows[Mp_max] (int2)
 struct PlanLayout {
-  size_t n_atoms, noff, poff, node_info, pair_info, dir_info, dir_mol, total;
+  size_t n_atoms, noff, poff, node_info, pair_info, dir_info, dir_mol, pair_rows, total;
 };
 PlanLayout plan_layout(int B, int N) {
   PlanLayout L;
@@ -41,6 +41,7 @@ PlanLayout plan_layout(int B, int N) {
   L.pair_info = o; o = al(o + size_t(B) * N * (N - 1) / 2 * 4 + 4);
   L.dir_info = o; o = al(o + size_t(B) * N * (N - 1) * 16 + 16);
   L.dir_mol = o; o = al(o + size_t(B) * N * (N - 1) * 4 + 4);
+  L.pair_rows = o; o = al(o + size_t(B) * N * (N - 1) / 2 * 8 + 8);
   L.total = o;
   return L;
 }
@@ -57,6 +58,7 @@ int make_plan(const void* plan_dev, int B, int N, int Mn, int Mp, Plan* p) {
   p->pair_info = reinterpret_cast<const uint32_t*>(base + L.pair_info);
   p->dir_info = reinterpret_cast<const int4*>(base + L.dir_info);
   p->dir_mol = reinterpret_cast<const uint32_t*>(base + L.dir_mol);
+  p->pair_rows = reinterpret_cast<const int2*>(base + L.pair_rows);
   return DS_OK;
 }
 
@@ -116,6 +118,7 @@ int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_d
   uint32_t* pi = reinterpret_cast<uint32_t*>(host.data() + L.pair_info);
   int4* di = reinterpret_cast<int4*>(host.data() + L.dir_info);
   uint32_t* dm = reinterpret_cast<uint32_t*>(host.data() + L.dir_mol);
+  int2* prw = reinterpret_cast<int2*>(host.data() + L.pair_rows);
   int mn = 0, mp = 0;
   for (int b = 0; b < B; ++b) {
     const int n = n_atoms_host[b];
@@ -126,7 +129,10 @@ int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_d
     for (int i = 0; i < n; ++i) ni[mn + i] = (static_cast<uint32_t>(b) << 6) | i;
     int q = mp;
     for (int i = 0; i < n; ++i)
-      for (int j = i + 1; j < n; ++j) pi[q++] = (static_cast<uint32_t>(b) << 12) | (i << 6) | j;
+      for (int j = i + 1; j < n; ++j) {
+        prw[q] = make_int2(mn + i, mn + j);
+        pi[q++] = (static_cast<uint32_t>(b) << 12) | (i << 6) | j;
+      }
     for (int r = 0; r < n; ++r)
       for (int c = 0; c < n; ++c) {
         if (c == r) continue;

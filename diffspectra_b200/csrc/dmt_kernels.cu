@@ -1016,10 +1016,14 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     if (Mp > 0) {
       // ---- pair chain B: residual + LN -> FFN -> residual; pair part of input_lin; skip projection
       ctx->cta_cap = ecap;
+      if (kFast && (ctx->fuse_mask & 64)) {
+        // the whole edge stream of the block in one kernel: e1 / f3 never leave the SM
+        DS_TRY(edge_ffn_launch(ctx, plan, w.e, X + 64, 128, w.pn, bw.n2e_b, ada_l, bw.ff3_w, bw.ff3_b, bw.ff4_w, bw.ff4_b, se));
+      } else {
       ds_launch(k_edge_update1<AT, kFast>, dim3(cdiv(Mp, 16)), dim3(256), 0, se, plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
                                                             reinterpret_cast<AT*>(w.e1b));
       LAUNCH_CHECK(ctx);
-      DS_TRY(linear(ctx, w.e1b, 64, bw.ff3_w, 64, bw.ff3_b, nullptr, 0, w.f3, 128, AD, Mp, 128, 64, ACT_SILU, se));
+      DS_TRY(linear(ctx, w.e1b, 64, bw.ff3_w, 64, bw.ff3_b, nullptr, 0, w.f3, 128, AD, Mp, 128, 64, kFast ? ACT_SILU_HALF : ACT_SILU, se));
       if (kFast && (ctx->fuse_mask & 4)) {
         GemmDesc g;   // e = e1 + gate * FFN(e1) -> fp32 stream and the [dist | e] operand
         g.A = w.f3; g.lda = 128; g.W = bw.ff4_w; g.ldw = 128; g.bias = bw.ff4_b; g.out = w.e; g.ldo = 64;
@@ -1031,6 +1035,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         DS_TRY(linear(ctx, w.f3, 128, bw.ff4_w, 128, bw.ff4_b, nullptr, 0, w.y1, 64, DT_F32, Mp, 64, 128, ACT_NONE, se));
         ds_launch(k_edge_update2<AT>, dim3(cdiv(Mp, 8)), dim3(256), 0, se, plan, w.e1f, w.y1, w.ada, l, w.e, X);
         LAUNCH_CHECK(ctx);
+      }
       }
       DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, se));
       // skip connection into the edge heads (dmt.py:387-388)

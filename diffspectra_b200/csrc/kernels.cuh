@@ -168,6 +168,10 @@ int coord_fused_launch(DsContext* ctx, const Plan& plan, const void* ab, const v
                        const uint8_t* pflags, const void* wc1, const float* bc1, const float* wc2, float* wdir,
                        cudaStream_t s);
 
+// fused edge-stream update of one block (edge_ffn_tc.cu): residual + LN + modulate -> ff3 -> SiLU -> ff4 -> gated residual
+int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ldx, const float* pn, const float* n2e_b,
+                    const float* ada_l, const void* w3, const float* b3, const void* w4, const float* b4, cudaStream_t s);
+
 int launch_pack_dense(DsContext* ctx, const Plan& plan, const float* x, const float* ex, float* xs, float* es,
                       cudaStream_t s);
 int launch_unpack_dense(DsContext* ctx, const Plan& plan, const float* xs, const float* es, float* x, float* ex,

@@ -179,8 +179,9 @@ int build(Packer& P, PackedWeights& pw) {
     b.ff1_b = P.vec(p + "ff_linear1.bias", 512);
     b.ff2_w = P.mat(p + "ff_linear2.weight", 256, 512);
     b.ff2_b = P.vec(p + "ff_linear2.bias", 256);
-    b.ff3_w = P.mat(p + "ff_linear3.weight", 128, 64);
-    b.ff3_b = P.vec(p + "ff_linear3.bias", 128);
+    // bf16 mode: ff_linear3 is stored halved like coord_mlp.0 (its SiLU runs as h + h tanh(h), ACT_SILU_HALF)
+    b.ff3_w = P.mat(p + "ff_linear3.weight", 128, 64, P.bf ? 0.5f : 1.0f);
+    b.ff3_b = P.vec(p + "ff_linear3.bias", 128, P.bf ? 0.5f : 1.0f);
     b.ff4_w = P.mat(p + "ff_linear4.weight", 64, 128);
     b.ff4_b = P.vec(p + "ff_linear4.bias", 64);
     // equi_update.input_lin [256, 640]: columns = [h_row(256) | h_col(256) | e(64) | dist(64)]
