@@ -272,10 +272,10 @@ int coord_fused_launch(DsContext* ctx, const Plan& plan, const void* ab, const v
   const int Md = 2 * plan.Mp;
   if (Md <= 0) return DS_OK;
   DS_CHECK(plan.dir_info != nullptr, DS_ERR_INVALID, "coord_fused: plan has no directed-edge table");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};            // the attribute is per device: one flag per device ordinal
+  if (!attr_set[ctx->device & 63]) {
     DS_CUDA_CHECK(cudaFuncSetAttribute(coord_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set = true;
+    attr_set[ctx->device & 63] = true;
   }
   CUtensorMap tmW;
   DS_TRY(ds_make_tmap_2d(ctx, &tmW, wc1, TK, TK, TK, KB, TK, false));

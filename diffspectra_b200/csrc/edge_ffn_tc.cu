@@ -335,10 +335,10 @@ int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ld
                     const float* ada_l, const void* w3, const float* b3, const void* w4, const float* b4, cudaStream_t s) {
   if (plan.Mp <= 0) return DS_OK;
   DS_CHECK(plan.pair_rows != nullptr, DS_ERR_INVALID, "edge_ffn: plan has no pair-row table");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};            // the attribute is per device: one flag per device ordinal
+  if (!attr_set[ctx->device & 63]) {
     DS_CUDA_CHECK(cudaFuncSetAttribute(edge_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    attr_set = true;
+    attr_set[ctx->device & 63] = true;
   }
   CUtensorMap tmW3, tmW4;
   DS_TRY(ds_make_tmap_2d(ctx, &tmW3, w3, 128, 64, 64, 64, 128, false));

@@ -476,10 +476,10 @@ int make_tmap(DsContext* ctx, CUtensorMap* map, const void* base, int rows, int 
 template <int BN, int MODE, bool TMA_OUT>
 int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
   using C = Cfg<BN, MODE, TMA_OUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};            // the attribute is per device: one flag per device ordinal
+  if (!attr_set[ctx->device & 63]) {
     DS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
+    attr_set[ctx->device & 63] = true;
   }
   CUtensorMap tmA, tmW, tmO, tmR, tmF;
   DS_TRY(make_tmap(ctx, &tmA, g.A, g.M, g.K, g.lda, BK, BM));
