@@ -730,6 +730,95 @@ __global__ void __launch_bounds__(256) k_coord_ln(Plan plan, const AT* __restric
   }
 }
 
+// Production (bf16) form of k_coord_ln with a register-free prefetch: each warp keeps the B[c] and G[pair] rows of its
+// next kCoordDepth targets in flight as 16-byte cp.async copies into a private shared-memory ring, so the bytes in
+// flight per SM (6 CTAs x 8 warps x 4 rows x 1 KB = 192 KB) no longer depend on the register budget.  Lane l owns the 8
+// contiguous channels [8l, 8l+8) - exactly the 16 bytes it copied - so no cross-lane visibility is needed.
+constexpr int kCoordDepth = 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void unpack8c(const uint4& u, float (&v)[8]) {
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+  v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+  v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* __restrict__ ab, const bf16* __restrict__ gp,
+                                                        const float* __restrict__ ada, int l, const uint8_t* __restrict__ pflags,
+                                                        bf16* __restrict__ Z, uint8_t* __restrict__ dflags) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) uint4 ring[8][kCoordDepth][2][32];      // [warp][slot][B | G][lane]
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + wi;
+  if (m >= plan.Mn) return;
+  const uint32_t info = plan.node_info[m];
+  const int mol = info >> 6, r = info & 63;
+  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_COORD;
+  float a[8], sh[8], sc[8];
+  {
+    uint4 u = *reinterpret_cast<const uint4*>(ab + static_cast<size_t>(m) * 512 + 8 * lane);
+    unpack8c(u, a);
+    const float4 s0 = *reinterpret_cast<const float4*>(ar + 8 * lane), s1 = *reinterpret_cast<const float4*>(ar + 8 * lane + 4);
+    const float4 c0 = *reinterpret_cast<const float4*>(ar + 256 + 8 * lane), c1 = *reinterpret_cast<const float4*>(ar + 256 + 8 * lane + 4);
+    sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+    sc[0] = 1.f + c0.x; sc[1] = 1.f + c0.y; sc[2] = 1.f + c0.z; sc[3] = 1.f + c0.w;
+    sc[4] = 1.f + c1.x; sc[5] = 1.f + c1.y; sc[6] = 1.f + c1.z; sc[7] = 1.f + c1.w;
+  }
+  const size_t d0 = static_cast<size_t>(2 * pbase) + static_cast<size_t>(r) * (n - 1);
+  auto issue = [&](int cc) {                 // start the copies of target number cc (if any) and close its group
+    if (cc < n - 1) {
+      const int c = cc + (cc >= r ? 1 : 0);
+      const int p = pbase + (r < c ? pair_index(n, r, c) : pair_index(n, c, r));
+      cp_async16(&ring[wi][cc % kCoordDepth][0][lane], ab + static_cast<size_t>(base + c) * 512 + 256 + 8 * lane);
+      cp_async16(&ring[wi][cc % kCoordDepth][1][lane], gp + static_cast<size_t>(p) * 256 + 8 * lane);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int k = 0; k < kCoordDepth; ++k) issue(k);
+  for (int cc = 0; cc < n - 1; ++cc) {
+    cp_async_wait<kCoordDepth - 1>();
+    float v[8], g[8];
+    unpack8c(ring[wi][cc % kCoordDepth][0][lane], v);
+    unpack8c(ring[wi][cc % kCoordDepth][1][lane], g);
+    issue(cc + kCoordDepth);                 // the slot just read is free again (this lane only touches its own 16 bytes)
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = (a[k] + v[k]) + g[k];
+      s += v[k];
+    }
+    const float mean = warp_sum(s) * (1.0f / 256.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] -= mean;
+      q = fmaf(v[k], v[k], q);
+    }
+    const float is = rsqrtf(warp_sum(q) * (1.0f / 256.0f) + kLnEps);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (v[k] * is) * sc[k] + sh[k];
+    uint4 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[0], v[1]));
+    o.y = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[2], v[3]));
+    o.z = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[4], v[5]));
+    o.w = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[6], v[7]));
+    *reinterpret_cast<uint4*>(Z + (d0 + cc) * 256 + 8 * lane) = o;
+    if (lane == 0) {
+      const int c = cc + (cc >= r ? 1 : 0);
+      dflags[d0 + cc] = pflags[pbase + (r < c ? pair_index(n, r, c) : pair_index(n, c, r))];
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // w[d] = mean(tanh(coord_mlp.2(u1[d])) * [1, adj2d, adjsp])   (dmt.py:46-51)
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_coord_out(Plan plan, const AT* __restrict__ u1, const float* __restrict__ wc2,
@@ -1049,8 +1138,12 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         // whole coordinate head in one kernel: the LN+modulate operand never leaves the SM
         DS_TRY(coord_fused_launch(ctx, plan, w.ab, w.gp, ada_l, w.pflags, bw.wc1, bw.bc1, bw.wc2, w.wdir, s));
       } else {
-        ds_launch(k_coord_ln<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.ab), reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
-                  reinterpret_cast<AT*>(w.Z), dflags);
+        if (kFast && (ctx->fuse_mask & 32))
+          ds_launch(k_coord_ln_async, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const bf16*>(w.ab),
+                    reinterpret_cast<const bf16*>(w.gp), w.ada, l, w.pflags, reinterpret_cast<bf16*>(w.Z), dflags);
+        else
+          ds_launch(k_coord_ln<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.ab), reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
+                    reinterpret_cast<AT*>(w.Z), dflags);
         LAUNCH_CHECK(ctx);
         if (kFast && (ctx->fuse_mask & 8)) {
           GemmDesc g;   // coord_mlp.0 -> SiLU -> coord_mlp.2 -> tanh -> adjacency-weighted mean, all in the epilogue
