@@ -309,7 +309,7 @@ def workload_name(args):
 
 def _demangle(name):
     import re
-    m = re.search(r'\d+(k_[a-z0-9_]+|gemm_tc_kernel|gemm_simt_kernel|coord_fused_kernel)', name)
+    m = re.search(r'\d+(k_[a-z0-9_]+|gemm_tc_kernel|gemm_simt_kernel|coord_fused_kernel|edge_ffn_kernel)', name)
     base = m.group(1) if m else name[:40]
     t = re.search(r'gemm_tc_kernelILi(\d+)ELi(\d+)ELb(\d)E', name)
     if t:
@@ -319,8 +319,8 @@ def _demangle(name):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (MB) from the committed `ncu --set full` capture of this
 # command at batch 1024 / QM9S histogram (profiles/r1_final_ncu.md); reported as roofline.traffic for the same workload only
-NCU_DRAM_MB = {'k_attention_grp': 215.2, 'k_coord_ln': 220.0, 'gemm_tc_kernel<256,COORD,0>': 173.7, 'k_edge_update1': 64.7,
-               'gemm_tc_kernel<64,RESGATE,1>': 101.6, 'gemm_tc_kernel<64,LNMOD,1>': 43.3}
+NCU_DRAM_MB = {'k_attention_grp': 215.1, 'k_coord_ln_async': 219.3, 'gemm_tc_kernel<256,COORD,0>': 171.8, 'edge_ffn_kernel': 68.2,
+               'gemm_tc_kernel<64,LNMOD,1>': 43.7}
 
 
 def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
@@ -349,6 +349,7 @@ def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
         'k_attention_grp': Mp * 1024 + Mp + Mn * (1536 + 256 * 6),          # e0|e1 once per pair, flags, q|k|v, hn fp32+bf16
         'k_wo_attention': Md * 1024 + Mn * (1536 + 512),
         'k_coord_ln': Mp * 512 + Mn * 1024 + Md * 513,                       # gp, ab in; Z + flags out
+        'edge_ffn_kernel': Mp * (256 + 256 + 128) + Mn * 256,               # e in, e out, bf16 copy out, hoisted node2edge rows
         'k_edge_update1': Mp * (256 + 256 + 128) + Mn * 256,
         'k_wo_edge_update1': Md * (256 + 256 + 128) + Mn * 512,
         'k_wo_dir_ln1': Md * (256 + 128),

@@ -1,7 +1,7 @@
 set -x
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1_final_n1.json 2> gpurun_out/bench_r1_final_n1.err; tail -2 gpurun_out/bench_r1_final_n1.err; head -c 700 gpurun_out/bench_r1_final_n1.json; echo
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r1_final_ref.json 2>/dev/null; head -c 400 gpurun_out/bench_r1_final_ref.json; echo
-python bench.py --model DMT_WO_EQ --steps 2 --warmup 1 > gpurun_out/bench_r1_final_wo_eq.json 2>/dev/null; head -c 300 gpurun_out/bench_r1_final_wo_eq.json; echo
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1_final_n1.json 2> gpurun_out/bench_r1_final_n1.err; tail -2 gpurun_out/bench_r1_final_n1.err; head -c 400 gpurun_out/bench_r1_final_n1.json; echo
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r1_final_ref.json 2>/dev/null; head -c 300 gpurun_out/bench_r1_final_ref.json; echo
+python bench.py --model DMT_WO_EQ --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_r1_final_wo_eq.json 2>/dev/null; head -c 300 gpurun_out/bench_r1_final_wo_eq.json; echo
 python bench.py --n-pad 64 --batch 512 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_r1_final_n64.json 2>/dev/null; head -c 300 gpurun_out/bench_r1_final_n64.json; echo
 python bench.py --steps 1 --warmup 1 --diffusion-steps 2 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 1700 --csv --log-file gpurun_out/launches_r1_final.csv python bench.py --steps 1 --warmup 1 --diffusion-steps 2 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_attention_grp|k_coord_ln|gemm_tc_kernel|k_edge_update1|k_rbf|k_pos_update|k_sampler|k_node" -s 300 -c 26 -o gpurun_out/prof_r1_final python bench.py --steps 1 --warmup 1 --diffusion-steps 2 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -c 200 gpurun_out/ncu_full.log
+ncu --set full --clock-control none --import-source on -k regex:"k_attention_grp|k_coord_ln|gemm_tc_kernel|edge_ffn|k_rbf|k_pos_update|k_sampler|k_node" -s 280 -c 24 -o gpurun_out/prof_r1_final python bench.py --steps 1 --warmup 1 --diffusion-steps 2 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -c 200 gpurun_out/ncu_full.log
