@@ -70,10 +70,13 @@ class AncestralSampler:
         net = _unwrap(model)
         if not isinstance(net, DMT_B200):
             raise TypeError('AncestralSampler (B200) drives a DMT_B200 model; got %s' % type(net).__name__)
-        eng = net.engine(z_T.device)
+        dev = z_T.device if z_T is not None else node_mask.device      # z_T None: initial noise drawn on the device (philox)
+        if z_T is None and self.noise != 'philox':
+            raise ValueError("z_T=None (device-drawn initial noise) needs noise='philox'")
+        eng = net.engine(dev)
         plan = net.plan_for(node_mask)
         ctx_emb = net.context_embedding(context)
-        coef = self.coefficients().to(z_T.device)
+        coef = self.coefficients().to(dev)
         steps = coef.shape[0]
         B, N = plan.B, plan.N
         if self.noise == 'philox':
@@ -83,7 +86,6 @@ class AncestralSampler:
             per_step = B * N * 9 * 4 + B * 2 * N * N * 4
             seg = max(1, min(steps, self.TORCH_NOISE_BUDGET // per_step))
             out, first = None, 0
-            dev = z_T.device
             while first < steps:
                 k = min(seg, steps - first)
                 rp = torch.empty(k, B, N, 3, device=dev)
@@ -184,11 +186,16 @@ def get_cond_sampling_eval_fn(config, noise_scheduler, batch_size, n_samples, in
                                    config.model.self_cond, None, config.eval.sampling_temperature, noise=noise, seed=seed,
                                    gid_base=gid0 + r * batch_size)
                 B, N = len(mols), node_mask.shape[1]
-                zx = torch.randn(B, N, 3, device=device) * node_mask
-                zx = zx - zx.sum(1, keepdim=True) / node_mask.sum(1, keepdim=True) * node_mask
-                z = torch.cat([zx, torch.randn(B, N, 6, device=device) * node_mask], dim=2)
-                ez = torch.randn(B, 2, N, N, device=device).tril(-1)
-                ez = (ez + ez.transpose(-1, -2)).permute(0, 2, 3, 1) * edge_mask.reshape(B, N, N, 1)
+                if noise == 'philox':
+                    # initial state drawn in the kernel too, keyed by the global molecule id: the whole trajectory is
+                    # invariant to how the test set is sharded over ranks / rounds
+                    z = ez = None
+                else:                                   # reference draw order (models/utils.py:67-106) from torch's generator
+                    zx = torch.randn(B, N, 3, device=device) * node_mask
+                    zx = zx - zx.sum(1, keepdim=True) / node_mask.sum(1, keepdim=True) * node_mask
+                    z = torch.cat([zx, torch.randn(B, N, 6, device=device) * node_mask], dim=2)
+                    ez = torch.randn(B, 2, N, N, device=device).tril(-1)
+                    ez = (ez + ez.transpose(-1, -2)).permute(0, 2, 3, 1) * edge_mask.reshape(B, N, N, 1)
                 x_node, x_edge = sampler.sampling(model, z, node_mask, edge_mask, ez, context)
                 pos, one_hot, fc, edge_types = post_process(x_node, 5, True, node_mask, inverse_scaler, x_edge, edge_mask,
                                                             True, model=model)

@@ -7,6 +7,7 @@ import torch
 from oracle import dense_oracle as O
 from oracle import philox_ref as P
 from oracle import weights as W
+from diffspectra_b200.noise_schedule import NoiseScheduleVP
 from tests.helpers import build_model, load_golden, max_abs, rel_l2
 
 pytestmark = pytest.mark.gpu
@@ -193,3 +194,54 @@ def test_bf16_free_running_sampling_quality():
     print('bf16 50-step x_mean rel %.2e edge rel %.2e' % (rel_l2(x_mean, g['x_mean']), rel_l2(e_mean, g['edge_x_mean'])))
     assert torch.isfinite(x_mean).all() and torch.isfinite(e_mean).all()
     assert rel_l2(x_mean, g['x_mean']) < 5e-2 and rel_l2(e_mean, g['edge_x_mean']) < 5e-2
+
+
+class _FakeMol:
+    """Stand-in for one item of the reference's QM9SDataset (datasets/qm9s_dataset.py): only the attributes the eval
+    driver touches (sampling.py:397-427)."""
+
+    def __init__(self, n, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.num_atom = torch.tensor(n)
+        self.pos = torch.randn(n, 3, generator=g)
+        self.rdmol = None
+        self.uv = torch.log10(1 + 50 * torch.rand(1, 701, generator=g))
+        self.ir = torch.log10(1 + 50 * torch.rand(1, 3501, generator=g))
+        self.raman = torch.log10(1 + 50 * torch.rand(1, 3501, generator=g))
+
+
+def test_eval_driver_contract_and_rank_sharding():
+    """get_cond_sampling_eval_fn (sampling.py:353-468): three lists truncated to n_samples, tuples shaped like
+    mol_process's; with Philox noise the union of the rank shards equals the single-rank result."""
+    from diffspectra_b200.config import get_config
+    from diffspectra_b200.sampling import get_cond_sampling_eval_fn
+    cfg = get_config('allspectra', device='cuda', precision='bf16')
+    cfg.sampling.steps = 5
+    model = build_model('allspectra', salt=1, coord_scale=0.02, precision='bf16')
+    ns = NoiseScheduleVP('cosine', continuous_beta_0=0.1, continuous_beta_1=20.)
+    n_list = W.sample_n_atoms(40, seed=3, force_first_max=False)
+    ds = [_FakeMol(int(n), 100 + i) for i, n in enumerate(n_list)]
+    n_samples, batch = 21, 8
+
+    def run(rank, world):
+        fn = get_cond_sampling_eval_fn(cfg, ns, batch, n_samples, None, ds, noise='philox', seed=5, rank=rank, world_size=world)
+        return fn(model)
+
+    mols, tpos, trd = run(0, 1)
+    assert len(mols) == n_samples and len(tpos) == n_samples and len(trd) == n_samples
+    torch.manual_seed(42)
+    perm = torch.randperm(len(ds))[:n_samples]
+    for k, (pos, atom, bond, fc) in enumerate(mols):
+        n = int(ds[int(perm[k])].num_atom)
+        assert pos.shape == (n, 3) and atom.shape == (n,) and bond.shape == (n, n) and fc.shape == (n,)
+        assert torch.equal(tpos[k], ds[int(perm[k])].pos)
+        assert atom.dtype == torch.int64 and fc.dtype == torch.int64 and pos.device.type == 'cpu'
+        assert torch.equal(bond, bond.t()) and bond.min() >= 0 and bond.max() <= 3 and int(atom.max()) < 5
+    # two ranks: contiguous shards of the permuted list, same molecules
+    shards = run(0, 2)[0] + run(1, 2)[0]
+    assert len(shards) == n_samples
+    same = 0
+    for a, b in zip(mols, shards):
+        assert a[0].shape == b[0].shape
+        same += int(torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and (a[0] - b[0]).abs().max() < 1e-3)
+    assert same >= n_samples - 1        # identical noise per global molecule id; bf16 tiles cut differently
