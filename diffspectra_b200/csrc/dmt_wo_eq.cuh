@@ -111,14 +111,33 @@ __global__ void __launch_bounds__(256) k_wo_attention(Plan plan, int ngrp, const
     const AT* er = ekv + (dbase + static_cast<size_t>(i) * (n - 1) + (j - (j > i ? 1 : 0))) * E01_LD + hh * 32;
     const float* qr = &sq[jl][hh * 16];
     float a = 0.f;
+    if constexpr (sizeof(AT) == 2) {
+      // 16 channels = two 16-byte loads per operand, all four in flight; k + ek as packed bf16 adds, q and the sum fp32
+      const uint4 k0 = *reinterpret_cast<const uint4*>(kr), k1 = *reinterpret_cast<const uint4*>(kr + 8);
+      const uint4 e0 = *reinterpret_cast<const uint4*>(er), e1 = *reinterpret_cast<const uint4*>(er + 8);
+      const __nv_bfloat162* kp0 = reinterpret_cast<const __nv_bfloat162*>(&k0);
+      const __nv_bfloat162* kp1 = reinterpret_cast<const __nv_bfloat162*>(&k1);
+      const __nv_bfloat162* ep0 = reinterpret_cast<const __nv_bfloat162*>(&e0);
+      const __nv_bfloat162* ep1 = reinterpret_cast<const __nv_bfloat162*>(&e1);
 #pragma unroll
-    for (int d = 0; d < 16; d += 4) {
-      const float4 kv = load4<AT>(kr + d), ev = load4<AT>(er + d);
-      const float4 qv = *reinterpret_cast<const float4*>(qr + d);
-      a = fmaf(qv.x, kv.x + ev.x, a);
-      a = fmaf(qv.y, kv.y + ev.y, a);
-      a = fmaf(qv.z, kv.z + ev.z, a);
-      a = fmaf(qv.w, kv.w + ev.w, a);
+      for (int d = 0; d < 4; ++d) {
+        const float2 s0 = __bfloat1622float2(__hadd2(kp0[d], ep0[d])), s1 = __bfloat1622float2(__hadd2(kp1[d], ep1[d]));
+        const float2 q0 = *reinterpret_cast<const float2*>(qr + 2 * d), q1 = *reinterpret_cast<const float2*>(qr + 8 + 2 * d);
+        a = fmaf(q0.x, s0.x, a);
+        a = fmaf(q0.y, s0.y, a);
+        a = fmaf(q1.x, s1.x, a);
+        a = fmaf(q1.y, s1.y, a);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < 16; d += 4) {
+        const float4 kv = load4<AT>(kr + d), ev = load4<AT>(er + d);
+        const float4 qv = *reinterpret_cast<const float4*>(qr + d);
+        a = fmaf(qv.x, kv.x + ev.x, a);
+        a = fmaf(qv.y, kv.y + ev.y, a);
+        a = fmaf(qv.z, kv.z + ev.z, a);
+        a = fmaf(qv.w, kv.w + ev.w, a);
+      }
     }
     slog[jl][i][hh] = a * 0.25f;                         // 1 / sqrt(out_channels = 16)
   }
@@ -151,11 +170,23 @@ __global__ void __launch_bounds__(256) k_wo_attention(Plan plan, int ngrp, const
       const float al = slog[w][i][hh];
       const AT* vr = qkv + static_cast<size_t>(base + i) * QKV_LD + hh * 48 + 32 + d0;
       const AT* er = ekv + (dbase + static_cast<size_t>(i) * (n - 1) + (j - (j > i ? 1 : 0))) * E01_LD + hh * 32 + 16 + d0;
-      const float4 v0 = load4<AT>(vr), v1 = load4<AT>(vr + 4), e0 = load4<AT>(er), e1 = load4<AT>(er + 4);
-      acc[0] = fmaf(al, v0.x + e0.x, acc[0]); acc[1] = fmaf(al, v0.y + e0.y, acc[1]);
-      acc[2] = fmaf(al, v0.z + e0.z, acc[2]); acc[3] = fmaf(al, v0.w + e0.w, acc[3]);
-      acc[4] = fmaf(al, v1.x + e1.x, acc[4]); acc[5] = fmaf(al, v1.y + e1.y, acc[5]);
-      acc[6] = fmaf(al, v1.z + e1.z, acc[6]); acc[7] = fmaf(al, v1.w + e1.w, acc[7]);
+      if constexpr (sizeof(AT) == 2) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(vr), ee = *reinterpret_cast<const uint4*>(er);
+        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv);
+        const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&ee);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 sv = __bfloat1622float2(__hadd2(v2[k], e2[k]));
+          acc[2 * k] = fmaf(al, sv.x, acc[2 * k]);
+          acc[2 * k + 1] = fmaf(al, sv.y, acc[2 * k + 1]);
+        }
+      } else {
+        const float4 v0 = load4<AT>(vr), v1 = load4<AT>(vr + 4), e0 = load4<AT>(er), e1 = load4<AT>(er + 4);
+        acc[0] = fmaf(al, v0.x + e0.x, acc[0]); acc[1] = fmaf(al, v0.y + e0.y, acc[1]);
+        acc[2] = fmaf(al, v0.z + e0.z, acc[2]); acc[3] = fmaf(al, v0.w + e0.w, acc[3]);
+        acc[4] = fmaf(al, v1.x + e1.x, acc[4]); acc[5] = fmaf(al, v1.y + e1.y, acc[5]);
+        acc[6] = fmaf(al, v1.z + e1.z, acc[6]); acc[7] = fmaf(al, v1.w + e1.w, acc[7]);
+      }
     }
     AT* o = out + static_cast<size_t>(base + j) * 256 + hh * 16 + d0;
     store4<AT>(o, acc[0], acc[1], acc[2], acc[3]);
