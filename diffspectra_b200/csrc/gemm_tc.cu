@@ -26,6 +26,10 @@ constexpr int BK = 64;    // one 128-byte swizzle atom of bf16
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
+// COORD mode is bound by its epilogue (7 CUDA-core instructions per accumulator element on two warps per scheduler), so it
+// gets eight more epilogue warps: warps 10-17 take columns [128, 256) of the rows that warps 0-7 share with them
+template <int MODE>
+constexpr int threads_for() { return (kEpiWarps + 2 + (MODE == GEMM_COORD ? 8 : 0)) * 32; }
 constexpr int kStageBox = 32 * 128;   // one staging box: 32 rows x 128 bytes
 
 template <int BN, int MODE, bool TMA_OUT>
@@ -36,7 +40,7 @@ struct Cfg {
   // per-warp staging: bf16 TMA-store boxes (2 x 4 KB), RESGATE: fp32 in/out tile (2 boxes) + one bf16 box
   static constexpr int kWarpStaging = (MODE == GEMM_RESGATE) ? 3 * kStageBox : (TMA_OUT ? 2 * kStageBox : 0);
   static constexpr int kStagingBytes = kEpiWarps * kWarpStaging;
-  static constexpr int kAuxBytes = 2 * 256 * 4 /*bias, per group*/ + (MODE == GEMM_COORD ? 256 * 16 : 0) + 256 /*barriers*/;
+  static constexpr int kAuxBytes = 2 * 256 * 4 /*bias, per group*/ + (MODE == GEMM_COORD ? 2 * 256 * 16 : 0) + 256 /*barriers*/;
   static constexpr int kBudget = 220 * 1024 - kStagingBytes - kAuxBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
@@ -151,7 +155,7 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, float (&f)[CH]) {
 }
 
 template <int BN, int MODE, bool TMA_OUT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(threads_for<MODE>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ CUtensorMap tmF, Epi ep, int M, int N, int K) {
@@ -166,7 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* staging = smem + C::kStages * C::kStageBytes;                 // 1024-aligned (stage sizes are multiples of 1 KB)
   float* sbias = reinterpret_cast<float*>(staging + C::kStagingBytes);   // [2][256]
   float4* swc2 = reinterpret_cast<float4*>(sbias + 512);                 // COORD: [256] (w0, w1, w2, bias)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + 2048 + (MODE == GEMM_COORD ? 4096 : 0));
+  float4* spart = swc2 + 256;                                            // COORD: [2][128] partial sums of columns 128..255
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sbias) + 2048 + (MODE == GEMM_COORD ? 8192 : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tfull_bar = bars + 2 * C::kStages;
@@ -192,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 128);
+      ptx::mbar_init(&tempty_bar[i], MODE == GEMM_COORD ? 256 : 128);
     }
     for (int i = 0; i < 8; ++i) ptx::mbar_init(&rbar[i], 1);
     ptx::fence_barrier_init();
@@ -258,7 +263,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue: group g owns accumulator stage g and every second tile =====================
-    const int g = warp >> 2, wq = warp & 3;
+    const bool second = MODE == GEMM_COORD && warp >= 10;          // COORD: column half [128, 256)
+    const int g = MODE == GEMM_COORD ? (((warp < 8 ? warp : warp - 10) >> 2) & 1) : (warp >> 2), wq = warp & 3;
     const int gtid = threadIdx.x & 127;
     float* gb = sbias + g * 256;
     uint8_t* my_stage = staging + warp * C::kWarpStaging;
@@ -420,8 +426,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (row_ok) *reinterpret_cast<float2*>(ep.wdir + static_cast<size_t>(row) * 2) = make_float2(s0, s1);
       } else {   // GEMM_COORD, BN == N == 256
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        const int c_lo = second ? 128 : 0;
 #pragma unroll 1
-        for (int c = 0; c < 256; c += 32) {
+        for (int c = c_lo; c < c_lo + 128; c += 32) {
           float f[32];
           load_acc<32>(t_addr + c, f);
 #pragma unroll
@@ -433,7 +440,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             s2 = fmaf(v, w.z, s2);
           }
         }
-        if (row_ok) {
+        float4* sp = spart + g * 128 + wq * 32 + lane;
+        if (second) *sp = make_float4(s0, s1, s2, 0.f);
+        named_bar_sync(3 + g, 256);                     // the two warps of every row have met
+        if (!second) {
+          const float4 o = *sp;
+          s0 += o.x; s1 += o.y; s2 += o.z;
+        }
+        if (row_ok && !second) {
           const uint8_t fl = ep.pflags[row];            // per directed edge (k_coord_ln)
           const float a2 = (fl & 1) ? 1.f : 0.f, asp = (fl & 2) ? 1.f : 0.f;
           ep.wdir[row] = (act_tanh<true>(s0) + act_tanh<true>(s1) * a2 + act_tanh<true>(s2) * asp) / 3.0f;
@@ -504,7 +518,7 @@ int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
   const int grid = tiles < sms ? tiles : sms;
   if (g_ds_prof.on)   // shape tag for ds_profile_end: mode(3) | N(15) | K(16) | M(30)
     g_ds_prof.tag = (static_cast<long long>(MODE) << 61) | (static_cast<long long>(g.N) << 46) | (static_cast<long long>(g.K) << 30) | g.M;
-  ds_launch(gemm_tc_kernel<BN, MODE, TMA_OUT>, dim3(grid), dim3(kThreads), C::kSmemBytes, s, tmA, tmW, tmO, tmR, tmF, ep, g.M, g.N, g.K);
+  ds_launch(gemm_tc_kernel<BN, MODE, TMA_OUT>, dim3(grid), dim3(threads_for<MODE>()), C::kSmemBytes, s, tmA, tmW, tmO, tmR, tmF, ep, g.M, g.N, g.K);
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;
   return DS_OK;
