@@ -128,6 +128,16 @@ __global__ void k_root_pair_flags(Plan plan, const float* __restrict__ cond, con
   if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(&flags[0], 1);
 }
 
+// adjacency bits per DIRECTED edge (source-major rows), once per denoiser call: they only depend on the
+// self-conditioning inputs, so the eight coordinate heads share them
+__global__ void k_dir_flags(int Md, const int4* __restrict__ dir_info, const uint8_t* __restrict__ pflags,
+                            uint8_t* __restrict__ dflags) {
+  pdl_trigger();
+  pdl_wait();
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < Md) dflags[d] = pflags[dir_info[d].x];
+}
+
 // e = edge_emb([edge_x(2) | cond_edge(2) | RBF_root(r0)(64)])   (dmt.py:363-377); 32 pairs per block
 template <typename AT, bool kFast>
 __global__ void __launch_bounds__(256) k_root_pairs(Plan plan, const float* __restrict__ es, const float* __restrict__ cond,
@@ -749,8 +759,7 @@ __device__ __forceinline__ void unpack8c(const uint4& u, float (&v)[8]) {
   v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 __global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* __restrict__ ab, const bf16* __restrict__ gp,
-                                                        const float* __restrict__ ada, int l, const uint8_t* __restrict__ pflags,
-                                                        bf16* __restrict__ Z, uint8_t* __restrict__ dflags) {
+                                                        const float* __restrict__ ada, int l, bf16* __restrict__ Z) {
   pdl_trigger();
   pdl_wait();
   __shared__ __align__(16) uint4 ring[8][kCoordDepth][2][32];      // [warp][slot][B | G][lane]
@@ -759,7 +768,7 @@ __global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* _
   if (m >= plan.Mn) return;
   const uint32_t info = plan.node_info[m];
   const int mol = info >> 6, r = info & 63;
-  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
+  const int n = plan.n_atoms[mol], pbase = plan.poff[mol];
   const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_COORD;
   float a[8], sh[8], sc[8];
   {
@@ -772,12 +781,12 @@ __global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* _
     sc[4] = 1.f + c1.x; sc[5] = 1.f + c1.y; sc[6] = 1.f + c1.z; sc[7] = 1.f + c1.w;
   }
   const size_t d0 = static_cast<size_t>(2 * pbase) + static_cast<size_t>(r) * (n - 1);
+  const int4* di = plan.dir_info + d0;       // x = pair row, z = atom row of the target (plan table, no index arithmetic)
   auto issue = [&](int cc) {                 // start the copies of target number cc (if any) and close its group
     if (cc < n - 1) {
-      const int c = cc + (cc >= r ? 1 : 0);
-      const int p = pbase + (r < c ? pair_index(n, r, c) : pair_index(n, c, r));
-      cp_async16(&ring[wi][cc % kCoordDepth][0][lane], ab + static_cast<size_t>(base + c) * 512 + 256 + 8 * lane);
-      cp_async16(&ring[wi][cc % kCoordDepth][1][lane], gp + static_cast<size_t>(p) * 256 + 8 * lane);
+      const int4 t = __ldg(di + cc);
+      cp_async16(&ring[wi][cc % kCoordDepth][0][lane], ab + static_cast<size_t>(t.z) * 512 + 256 + 8 * lane);
+      cp_async16(&ring[wi][cc % kCoordDepth][1][lane], gp + static_cast<size_t>(t.x) * 256 + 8 * lane);
     }
     cp_async_commit();
   };
@@ -785,36 +794,43 @@ __global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* _
   for (int k = 0; k < kCoordDepth; ++k) issue(k);
   for (int cc = 0; cc < n - 1; ++cc) {
     cp_async_wait<kCoordDepth - 1>();
-    float v[8], g[8];
-    unpack8c(ring[wi][cc % kCoordDepth][0][lane], v);
-    unpack8c(ring[wi][cc % kCoordDepth][1][lane], g);
-    issue(cc + kCoordDepth);                 // the slot just read is free again (this lane only touches its own 16 bytes)
-    float s = 0.f;
+    // B[c] + G[pair] as four packed bf16 adds (both operands are bf16 already), then fp32: + A[r], statistics, modulate
+    uint4 bg;
+    {
+      const uint4 bq = ring[wi][cc % kCoordDepth][0][lane], gq = ring[wi][cc % kCoordDepth][1][lane];
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bq);
+      const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gq);
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&bg);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      v[k] = (a[k] + v[k]) + g[k];
-      s += v[k];
+      for (int k = 0; k < 4; ++k) o2[k] = __hadd2(b2[k], g2[k]);
     }
-    const float mean = warp_sum(s) * (1.0f / 256.0f);
-    float q = 0.f;
+    issue(cc + kCoordDepth);                 // the slot just read is free again (this lane only touches its own 16 bytes)
+    float v[8];
+    unpack8c(bg, v);
+    float s = 0.f, q = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      v[k] -= mean;
+      v[k] += a[k];
+      s += v[k];
       q = fmaf(v[k], v[k], q);
     }
-    const float is = rsqrtf(warp_sum(q) * (1.0f / 256.0f) + kLnEps);
+    // both reductions in flight together; var = E[y^2] - mean^2 in fp32 (|y| = O(1))
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (v[k] * is) * sc[k] + sh[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const float mean = s * (1.0f / 256.0f);
+    const float is = rsqrtf(fmaxf(q * (1.0f / 256.0f) - mean * mean, 0.f) + kLnEps);
+    const float nm = -mean * is;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], is, nm) * sc[k] + sh[k];
     uint4 o;
     o.x = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[0], v[1]));
     o.y = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[2], v[3]));
     o.z = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[4], v[5]));
     o.w = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[6], v[7]));
     *reinterpret_cast<uint4*>(Z + (d0 + cc) * 256 + 8 * lane) = o;
-    if (lane == 0) {
-      const int c = cc + (cc >= r ? 1 : 0);
-      dflags[d0 + cc] = pflags[pbase + (r < c ? pair_index(n, r, c) : pair_index(n, c, r))];
-    }
   }
   cp_async_wait<0>();
 }
@@ -1022,6 +1038,10 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
 
   const int ngrp = (plan.N + ATT_G - 1) / ATT_G;
   uint8_t* dflags = w.pflags + (Mp > 0 ? Mp : 1);      // adjacency bits per directed edge (source-major order)
+  if (kFast && (ctx->fuse_mask & 32) && Mp > 0) {
+    ds_launch(k_dir_flags, dim3(cdiv(Md, 256)), dim3(256), 0, s, Md, plan.dir_info, w.pflags, dflags);
+    LAUNCH_CHECK(ctx);
+  }
 
   // Two chains per block share nothing until they meet (attention, coordinate head): the atom-side kernels go to a
   // side stream (graph branch) with a small persistent-GEMM grid, the pair-side kernels keep the rest of the SMs.
@@ -1140,7 +1160,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       } else {
         if (kFast && (ctx->fuse_mask & 32))
           ds_launch(k_coord_ln_async, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const bf16*>(w.ab),
-                    reinterpret_cast<const bf16*>(w.gp), w.ada, l, w.pflags, reinterpret_cast<bf16*>(w.Z), dflags);
+                    reinterpret_cast<const bf16*>(w.gp), w.ada, l, reinterpret_cast<bf16*>(w.Z));
         else
           ds_launch(k_coord_ln<AT, kFast>, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const AT*>(w.ab), reinterpret_cast<const AT*>(w.gp), w.ada, l, w.pflags,
                     reinterpret_cast<AT*>(w.Z), dflags);
