@@ -414,6 +414,11 @@ __global__ void __launch_bounds__(256) k_node_ln1(Plan plan, const float* __rest
 // several CTAs are resident per SM; k / v rows and the e0|e1 pair rows are streamed through L1 with 32/64-bit
 // loads; per-target messages accumulate in registers (thread t <-> value channel t).
 constexpr int ATT_G = 8;
+// bf16x2 -> two fp32 in exactly two integer instructions (shift / mask); the library conversion compiles to four
+__device__ __forceinline__ float2 bf2_to_f2(__nv_bfloat162 h) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
 // 16-byte read-only load that the compiler may not sink next to its first use: a batch of these stays a batch,
 // so several rows are in flight per warp (the scheduler otherwise serialises load -> use pairs to save registers)
 __device__ __forceinline__ uint4 ldg128_pinned(const void* p) {
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
 #pragma unroll
         for (int d = 0; d < C_SUB / 2; ++d) {
           const float2 qv = *reinterpret_cast<const float2*>(qr + 2 * d);
-          const float2 ke = __bfloat1622float2(__hmul2(ev[d], kv[d]));
+          const float2 ke = bf2_to_f2(__hmul2(ev[d], kv[d]));
           a = fmaf(qv.x, ke.x, a);
           a = fmaf(qv.y, ke.y, a);
         }
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
           const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&ee[u]);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float2 pr = __bfloat1622float2(__hmul2(v2[k], e2[k]));
+            const float2 pr = bf2_to_f2(__hmul2(v2[k], e2[k]));
             acc[2 * k] = fmaf(al[u], pr.x, acc[2 * k]);
             acc[2 * k + 1] = fmaf(al[u], pr.y, acc[2 * k + 1]);
           }
