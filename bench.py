@@ -319,8 +319,8 @@ def _demangle(name):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (MB) from the committed `ncu --set full` capture of this
 # command at batch 1024 / QM9S histogram (profiles/r1_final_ncu.md); reported as roofline.traffic for the same workload only
-NCU_DRAM_MB = {'k_attention_grp': 215.1, 'k_coord_ln_async': 219.3, 'gemm_tc_kernel<256,COORD,0>': 171.8, 'edge_ffn_kernel': 68.2,
-               'gemm_tc_kernel<64,LNMOD,1>': 43.7}
+NCU_DRAM_MB = {'k_attention_grp': 214.5, 'k_coord_ln_async': 226.3, 'gemm_tc_kernel<256,COORD,0>': 171.1, 'edge_ffn_kernel': 69.5,
+               'gemm_tc_kernel<64,LNMOD,1>': 43.1}
 
 
 def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
