@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
   typedef typename std::conditional<kFast, __half, float>::type LT;
   __shared__ LT slog[ATT_G][MAXN][N_HEADS];
   __shared__ int srow[ATT_G][MAXN];
+  __shared__ float sinv[ATT_G][N_HEADS];             // 1 / softmax denominator, applied once to the accumulated messages
   const int mol = blockIdx.x / ngrp, j0 = (blockIdx.x % ngrp) * ATT_G;
   const int n = plan.n_atoms[mol];
   if (j0 >= n) return;
@@ -511,8 +512,7 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
       slog[jl][i][hh] = static_cast<LT>(ex);
       den += ex;
     }
-    const float inv = 1.0f / (den + 1e-16f);
-    for (int i = 0; i < n; ++i) slog[jl][i][hh] = static_cast<LT>(static_cast<float>(slog[jl][i][hh]) * inv);
+    sinv[jl][hh] = 1.0f / (den + 1e-16f);
   }
   __syncthreads();
   // pass 2: messages; warp w <-> target j0 + w, lane <-> 8 value channels (one head per 2 lanes):
@@ -569,6 +569,11 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
         acc[4] = fmaf(al * v1.x, e1.x, acc[4]); acc[5] = fmaf(al * v1.y, e1.y, acc[5]);
         acc[6] = fmaf(al * v1.z, e1.z, acc[6]); acc[7] = fmaf(al * v1.w, e1.w, acc[7]);
       }
+    }
+    {
+      const float inv = sinv[w][hh];                   // sum_i (ex_i inv) x_i == inv sum_i ex_i x_i
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] *= inv;
     }
     float* ho = hn + static_cast<size_t>(base + j) * 256 + lane * 8;
     *reinterpret_cast<float4*>(ho) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -869,6 +874,7 @@ __global__ void __launch_bounds__(256) k_coord_out(Plan plan, const AT* __restri
 
 // pos_r += sum_c (pos_r - pos_c)/max(|.|,1e-8) * scale * w[r,c]; then centre-of-mass removal
 // (dmt.py:40-41,53-58, layers.py:344-347, dmt.py:385-386)
+template <bool kFast>
 __global__ void __launch_bounds__(64) k_pos_update(Plan plan, const float* __restrict__ wdir, const float* __restrict__ scale_p,
                                                    float* __restrict__ pos) {
   pdl_trigger();
@@ -891,11 +897,18 @@ __global__ void __launch_bounds__(64) k_pos_update(Plan plan, const float* __res
     for (int c = 0; c < n; ++c) {
       if (c == r) continue;
       const float dx = px - sp[c][0], dy = py - sp[c][1], dz = pz - sp[c][2];
-      const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
       const float w = wdir[static_cast<size_t>(2 * pbase) + r * (n - 1) + (c - (c > r ? 1 : 0))];
-      ax += (dx / nrm * scale) * w;
-      ay += (dy / nrm * scale) * w;
-      az += (dz / nrm * scale) * w;
+      if (kFast) {          // 1 / max(|d|, 1e-8) as one rsqrt, the three divisions become multiplies
+        const float f = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-16f)) * scale * w;
+        ax = fmaf(dx, f, ax);
+        ay = fmaf(dy, f, ay);
+        az = fmaf(dz, f, az);
+      } else {
+        const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
+        ax += (dx / nrm * scale) * w;
+        ay += (dy / nrm * scale) * w;
+        az += (dz / nrm * scale) * w;
+      }
     }
     nx = px + ax; ny = py + ay; nz = pz + az;
   }
@@ -1182,7 +1195,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         }
       }
     }
-    ds_launch(k_pos_update, dim3(B), dim3(64), 0, s, plan, w.wdir, bw.coord_scale, w.pos);
+    ds_launch(k_pos_update<kFast>, dim3(B), dim3(64), 0, s, plan, w.wdir, bw.coord_scale, w.pos);
     LAUNCH_CHECK(ctx);
   }
 
