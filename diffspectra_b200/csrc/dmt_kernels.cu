@@ -260,19 +260,32 @@ __global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict_
     coef[k] = 2.5066272160016134f * sd[k];       // (2*3.14159)**0.5 * std
     if (kFast) { sd[k] = 1.0f / sd[k]; coef[k] = 1.0f / coef[k]; }
   }
-#pragma unroll 1
+  // the four pairs of a thread: index tables first, then every dependent load, then the arithmetic (the three-deep
+  // load chain pair_info -> noff -> pos of a serial loop was the kernel's critical path)
+  int pp[4];
+  int2 rows[4];
+  uint32_t info[4];
+#pragma unroll
   for (int it = 0; it < 4; ++it) {
-    const int p = (blockIdx.x * 4 + it) * 32 + (threadIdx.x >> 3);
-    if (p >= plan.Mp) return;
-    int mol, i, j;
-    unpack_pair(plan.pair_info[p], mol, i, j);
-    const int base = plan.noff[mol];
-    const float* pi = pos + static_cast<size_t>(base + i) * 3;
-    const float* pj = pos + static_cast<size_t>(base + j) * 3;
+    pp[it] = (blockIdx.x * 4 + it) * 32 + (threadIdx.x >> 3);
+    const int pc = min(pp[it], plan.Mp - 1);
+    rows[it] = __ldg(plan.pair_rows + pc);
+    info[it] = __ldg(plan.pair_info + pc);
+  }
+  float xx[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const float* pi = pos + static_cast<size_t>(rows[it].x) * 3;
+    const float* pj = pos + static_cast<size_t>(rows[it].y) * 3;
+    const float* ar = ada + static_cast<size_t>(info[it] >> 12) * ADA_LD + l * ADA_BLK + ADA_RBF;
     const float dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
     const float r2 = dx * dx + dy * dy + dz * dz;
-    const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_RBF;
-    const float x = r2 * (ar[0] + 1.0f) + ar[1];
+    xx[it] = r2 * (ar[0] + 1.0f) + ar[1];
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    if (pp[it] >= plan.Mp) return;
+    const float x = xx[it];
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -285,7 +298,7 @@ __global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict_
       }
     }
     if (k0 == 0) v[0] = x;
-    AT* o = X + static_cast<size_t>(p) * 128 + k0;
+    AT* o = X + static_cast<size_t>(pp[it]) * 128 + k0;
     store4<AT>(o, v[0], v[1], v[2], v[3]);
     store4<AT>(o + 4, v[4], v[5], v[6], v[7]);
   }
@@ -440,7 +453,8 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
   __shared__ LT slog[ATT_G][MAXN][N_HEADS];
   __shared__ int srow[ATT_G][MAXN];
   __shared__ float sinv[ATT_G][N_HEADS];             // 1 / softmax denominator, applied once to the accumulated messages
-  const int mol = blockIdx.x / ngrp, j0 = (blockIdx.x % ngrp) * ATT_G;
+  // CTAs are issued largest molecule first (plan.mol_order), so the kernel's tail is made of its cheapest CTAs
+  const int mol = plan.mol_order[blockIdx.x / ngrp], j0 = (blockIdx.x % ngrp) * ATT_G;
   const int n = plan.n_atoms[mol];
   if (j0 >= n) return;
   const int t = threadIdx.x;
@@ -875,18 +889,23 @@ __global__ void __launch_bounds__(256) k_coord_out(Plan plan, const AT* __restri
 // pos_r += sum_c (pos_r - pos_c)/max(|.|,1e-8) * scale * w[r,c]; then centre-of-mass removal
 // (dmt.py:40-41,53-58, layers.py:344-347, dmt.py:385-386)
 template <bool kFast>
-__global__ void __launch_bounds__(64) k_pos_update(Plan plan, const float* __restrict__ wdir, const float* __restrict__ scale_p,
-                                                   float* __restrict__ pos) {
+__global__ void __launch_bounds__(128) k_pos_update(Plan plan, const float* __restrict__ wdir, const float* __restrict__ scale_p,
+                                                    float* __restrict__ pos) {
   pdl_trigger();
   pdl_wait();
+  // the n (n - 1) directed-edge weights of the molecule arrive with coalesced loads (one round trip to L2 instead of
+  // n - 1 dependent strided ones per thread); the pair loop then runs out of shared memory
+  __shared__ float sw[MAX_ATOMS * (MAX_ATOMS - 1)];
   __shared__ float sp[MAX_ATOMS][3];
-  __shared__ float red[3][2];
-  const int mol = blockIdx.x, r = threadIdx.x;
+  __shared__ float red[3][4];
+  const int mol = plan.mol_order[blockIdx.x], r = threadIdx.x;
   const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
-  if (r < n) {
-    sp[r][0] = pos[(base + r) * 3 + 0];
-    sp[r][1] = pos[(base + r) * 3 + 1];
-    sp[r][2] = pos[(base + r) * 3 + 2];
+  {
+    const float* wsrc = wdir + static_cast<size_t>(2) * pbase;
+    const int nd = n * (n - 1);
+    for (int idx = r; idx < nd; idx += 128) sw[idx] = wsrc[idx];
+    if (r < n * 3) (&sp[0][0])[r] = pos[static_cast<size_t>(base) * 3 + r];
+    if (r + 128 < n * 3) (&sp[0][0])[r + 128] = pos[static_cast<size_t>(base) * 3 + r + 128];
   }
   __syncthreads();
   float nx = 0.f, ny = 0.f, nz = 0.f;
@@ -894,10 +913,11 @@ __global__ void __launch_bounds__(64) k_pos_update(Plan plan, const float* __res
     const float scale = scale_p[0];
     const float px = sp[r][0], py = sp[r][1], pz = sp[r][2];
     float ax = 0.f, ay = 0.f, az = 0.f;
+    const float* wr = sw + r * (n - 1);
     for (int c = 0; c < n; ++c) {
       if (c == r) continue;
       const float dx = px - sp[c][0], dy = py - sp[c][1], dz = pz - sp[c][2];
-      const float w = wdir[static_cast<size_t>(2 * pbase) + r * (n - 1) + (c - (c > r ? 1 : 0))];
+      const float w = wr[c - (c > r ? 1 : 0)];
       if (kFast) {          // 1 / max(|d|, 1e-8) as one rsqrt, the three divisions become multiplies
         const float f = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-16f)) * scale * w;
         ax = fmaf(dx, f, ax);
@@ -1195,7 +1215,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         }
       }
     }
-    ds_launch(k_pos_update<kFast>, dim3(B), dim3(64), 0, s, plan, w.wdir, bw.coord_scale, w.pos);
+    ds_launch(k_pos_update<kFast>, dim3(B), dim3(128), 0, s, plan, w.wdir, bw.coord_scale, w.pos);
     LAUNCH_CHECK(ctx);
   }
 

@@ -181,19 +181,69 @@ class _B200Denoiser(nn.Module):
     def _init_plumbing(self, config):
         self.spectra_version = config.data.spectra_version
         self.precision = _cfg(config.model, 'b200_precision', 'bf16')          # 'bf16' (tcgen05) | 'fp32' (validation)
-        if _cfg(config.model, 'pretrained_specformer_path', ''):
-            raise NotImplementedError('pretrained SpecFormer loading (models/dmt.py:268-303) is outside the sampling '
-                                      'hot path; load the full checkpoint instead')
+        self._pretrained_specformer_path = _cfg(config.model, 'pretrained_specformer_path', '')
         self._engine = None
         self._weights_key = None
+        self._weights_fp = None
         self._plan_cache = {}
         self._ctx_cache = (None, None)
+
+    # ------------------------------------------------------------------ checkpoint ingestion
+    _SPECFORMER_PREFIXES = ('model.representation_spec_model', 'model.representation_model')
+
+    def _maybe_load_pretrained_specformer(self):
+        """Called at the end of the sub-class constructors, where the reference does it (models/dmt.py:263-267)."""
+        if self._pretrained_specformer_path:
+            self.load_pretrained_specformer(self._pretrained_specformer_path)
+
+    def load_pretrained_specformer(self, ckpt_path):
+        """Same rule as DMT.load_pretrained_specformer (models/dmt.py:268-303): the checkpoint's 'state_dict' holds the
+        encoder under the first prefix of _SPECFORMER_PREFIXES that occurs; every cond_encoder key whose prefixed
+        source exists with the same shape is taken (out_norm.* always from 'model.representation_model.out_norm.*'),
+        anything else keeps its initial value; a checkpoint without 'state_dict' or without a known prefix is ignored
+        with a warning, like in the reference.  Returns the number of tensors taken.  The packed kernel weights are
+        rebuilt lazily because load_state_dict bumps the parameter versions (see engine())."""
+        ckpt = torch.load(ckpt_path, map_location='cpu', weights_only=False)
+        if not isinstance(ckpt, dict) or 'state_dict' not in ckpt:
+            print("Warning: pretrained model does not contain 'state_dict' key. Loading the entire checkpoint.")
+            return 0
+        src = ckpt['state_dict']
+        prefix = next((p for p in self._SPECFORMER_PREFIXES if any(k.startswith(p) for k in src)), None)
+        if prefix is None:
+            print('Warning: No matching prefix found in the state_dict.')
+            return 0
+        own = self.cond_encoder.state_dict()
+        taken = {}
+        for key, cur in own.items():
+            if key in ('out_norm.weight', 'out_norm.bias'):
+                skey = 'model.representation_model.out_norm.' + key.rsplit('.', 1)[-1]
+            else:
+                skey = prefix + '.' + key
+            val = src.get(skey)
+            if val is not None and tuple(val.shape) == tuple(cur.shape):
+                taken[key] = val
+        if taken:
+            self.cond_encoder.load_state_dict(taken, strict=False)
+            print('Loaded %d keys from the pretrained SpecFormer model.' % len(taken))
+        else:
+            print('0 Warning: No matching keys found in the pretrained SpecFormer model.')
+        return len(taken)
 
     # ------------------------------------------------------------------ engine plumbing
     def _params_key(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
-    def engine(self, device=None):
+    def _fingerprint(self):
+        """Per-tensor L2 norms of every floating-point parameter / buffer, on their device.  `ema.copy_to` and
+        `ema.restore` (models/ema.py:52-55,74-76) write through `param.data.copy_`, which changes neither data_ptr nor
+        the autograd version counter, so the cheap key above cannot see them; this content check (a few multi-tensor
+        kernels over 130 MB + one 2.6 KB compare) runs once per sampling round, not per denoiser call."""
+        ts = [t.detach() for t in list(self.parameters()) + list(self.buffers()) if t.is_floating_point()]
+        return torch.stack(torch._foreach_norm(ts))
+
+    def engine(self, device=None, verify=False):
+        """verify=True additionally compares the content fingerprint of the weights with the one taken when they were
+        packed (used at the start of every sampling round)."""
         device = torch.device(device) if device is not None else next(self.parameters()).device
         if self._engine is None or self._engine.device != device or self._engine.mode_name != self.precision:
             self._engine = Engine(device, mode=self.precision, spectra_version=self.spectra_version, model_kind=self.MODEL_KIND)
@@ -201,11 +251,23 @@ class _B200Denoiser(nn.Module):
             self._plan_cache = {}
             self._ctx_cache = (None, None)
         key = self._params_key()
-        if key != self._weights_key:                     # load_state_dict / ema.copy_to / optimizer step happened
+        stale = key != self._weights_key                 # load_state_dict / optimizer step / .to() happened
+        fp = None
+        if verify and not stale:
+            fp = self._fingerprint()
+            stale = self._weights_fp is None or fp.shape != self._weights_fp.shape or not torch.equal(fp, self._weights_fp)
+        if stale:
             self._engine.pack_weights(self.state_dict())
             self._weights_key = key
+            self._weights_fp = fp if fp is not None else self._fingerprint()
             self._ctx_cache = (None, None)
         return self._engine
+
+    def invalidate_packed_weights(self):
+        """Force a re-pack at the next call (for callers that modify parameters through `.data` between calls of the
+        same sampling round)."""
+        self._weights_key = None
+        return self
 
     def set_precision(self, precision):
         assert precision in ('bf16', 'fp32')
@@ -234,8 +296,10 @@ class _B200Denoiser(nn.Module):
         across the 1000 steps of a sampling round; the reference recomputes them every call)."""
         ts = context if isinstance(context, (list, tuple)) else [context]
         key = tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in ts)
-        if self._ctx_cache[0] != key:
-            self._ctx_cache = (key, self.engine().context_embedding(context))
+        if self._ctx_cache[0] != key:                    # a new sampling round: also the point where weights are re-verified
+            self._ctx_cache = (None, None)
+            eng = self.engine(verify=True)
+            self._ctx_cache = (key, eng.context_embedding(context))
         return self._ctx_cache[1]
 
     # ------------------------------------------------------------------ reference interface
@@ -303,6 +367,7 @@ class DMT_B200(_B200Denoiser):
         self.cond_encoder = _SpecFormerParams(m.patch_len, m.stride, hidden_dim, d.spectra_version)
         self.cond_lin = nn.Linear(hidden_dim, time_dim)
         self._init_plumbing(config)
+        self._maybe_load_pretrained_specformer()
 
 
 class _NodeEmbedParams(nn.Module):             # models/dmt_wo_eq.py:629-637
@@ -368,6 +433,7 @@ class DMT_WO_EQ_B200(_B200Denoiser):
         self.cond_encoder = _SpecFormerParams(m.patch_len, m.stride, hidden_dim, d.spectra_version)
         self.cond_lin = nn.Linear(hidden_dim, time_dim)
         self._init_plumbing(config)
+        self._maybe_load_pretrained_specformer()
 
 
 def register(models_utils=None):

@@ -11,7 +11,7 @@ CUDA loop of libdiffspectra_b200.so.
 import numpy as np
 import torch
 
-from .model import DMT_B200
+from .model import _B200Denoiser
 from .noise_schedule import ancestral_coefficients
 
 
@@ -68,12 +68,12 @@ class AncestralSampler:
 
     def sampling(self, model, z_T, node_mask, edge_mask, edge_z_T=None, context=None):
         net = _unwrap(model)
-        if not isinstance(net, DMT_B200):
-            raise TypeError('AncestralSampler (B200) drives a DMT_B200 model; got %s' % type(net).__name__)
+        if not isinstance(net, _B200Denoiser):
+            raise TypeError('AncestralSampler (B200) drives a DMT_B200 / DMT_WO_EQ_B200 model; got %s' % type(net).__name__)
         dev = z_T.device if z_T is not None else node_mask.device      # z_T None: initial noise drawn on the device (philox)
         if z_T is None and self.noise != 'philox':
             raise ValueError("z_T=None (device-drawn initial noise) needs noise='philox'")
-        eng = net.engine(dev)
+        eng = net.engine(dev, verify=True)              # content check: ema.copy_to / ema.restore bypass version counters
         plan = net.plan_for(node_mask)
         ctx_emb = net.context_embedding(context)
         coef = self.coefficients().to(dev)

@@ -119,3 +119,20 @@ def test_inputs_not_mutated_and_weights_repack():
     nm, _ = W.make_masks(g['n_atoms'], g['N'])
     d = (pred2 - pred)[..., 3:].cpu()
     assert torch.allclose(d, torch.ones_like(d) * nm, atol=1e-5)
+
+
+def test_weights_changed_through_data_copy_are_repacked():
+    """run_lib.py:359-362 order is restore_checkpoint -> ema.copy_to -> sampling_fn; ema.copy_to / ema.restore write
+    through `param.data.copy_` (models/ema.py:52-55), invisible to version counters.  A model that has already run
+    (packed weights cached) must pick the new weights up at the next sampling round (= next new context)."""
+    g = load_golden('denoiser_ir.pt')
+    model = build_model('ir', g['salt'] + 11, g['coord_scale'], 'fp32')       # wrong weights first
+    _run_case(model, g, 'step0')
+    right = build_model('ir', g['salt'], g['coord_scale'], 'fp32', device='cpu').state_dict()
+    key = model._params_key()
+    with torch.no_grad():
+        for (n, p) in model.named_parameters():                              # what ema.copy_to does
+            p.data.copy_(right[n].data)
+    assert model._params_key() == key                                        # the cheap key is blind to it
+    pred, epred, c = _run_case(model, g, 'step0')                            # fresh context tensors = new round
+    assert rel_l2(pred, c['pred']) <= FP32_TOL and rel_l2(epred, c['edge_pred']) <= FP32_TOL

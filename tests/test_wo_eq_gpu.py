@@ -66,6 +66,13 @@ def test_wo_eq_sampling_trajectory_matches_reference():
     ex, ee = rel_l2(x_mean, t['x_mean']), rel_l2(e_mean, t['edge_x_mean'])
     print('wo_eq trajectory fp32: x %.2e edge %.2e' % (ex, ee))
     assert ex < 1e-4 and ee < 1e-4
+    # the sampler entry point itself (sampling.py:565) accepts the ablation model, bare or DataParallel-wrapped
+    ps = AncestralSampler(ns, torch.linspace(ns.T, 1e-3, 5), True, True, True, None, 1.0, noise='philox', seed=3)
+    with torch.no_grad():
+        a = ps.sampling(model, None, nm.cuda(), em.cuda(), None, ctx)
+        b = ps.sampling(torch.nn.DataParallel(model), None, nm.cuda(), em.cuda(), None, ctx)
+    assert torch.isfinite(a[0]).all() and torch.isfinite(a[1]).all()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
 def test_wo_eq_n64_and_large_batch():
