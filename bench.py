@@ -354,6 +354,7 @@ def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
         'k_wo_edge_update1': Md * (256 + 256 + 128) + Mn * 512,
         'k_wo_dir_ln1': Md * (256 + 128),
         'k_rbf': Mp * 128 + Mn * 12,
+        'k_pos_rbf': Mp * 128 + Md * 4 + Mn * 24,            # X[:, :64] out, directed-edge weights in, positions in/out
         'k_node_ln1': Mn * (1024 + 512), 'k_node_update1': Mn * (2048 + 1024 + 512), 'k_wo_node_update1': Mn * (2048 + 1024 + 512),
         'k_pos_update': Md * 4 + Mn * 24,
         'k_sampler_pairs': Mp * 24, 'k_sampler_nodes': Mn * 108,

@@ -242,6 +242,11 @@ __global__ void k_copy64(int rows, const AT* __restrict__ src, int src_ld, AT* _
 }
 
 // ----------------------------------------------------------------------------- per-block kernels
+__device__ __forceinline__ float ex2_approx(float x) {     // one MUFU.EX2; denormal results flush to zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // X[:, 0:64] = RBF_l(|pos_i - pos_j|^2)   (dmt.py:136-138); 8 threads per pair (8 channels each), 4 pairs per thread
 // with the per-channel Gaussian constants hoisted out of the pair loop
 template <typename AT, bool kFast>
@@ -301,6 +306,122 @@ __global__ void __launch_bounds__(256) k_rbf(Plan plan, const float* __restrict_
     AT* o = X + static_cast<size_t>(pp[it]) * 128 + k0;
     store4<AT>(o, v[0], v[1], v[2], v[3]);
     store4<AT>(o + 4, v[4], v[5], v[6], v[7]);
+  }
+}
+
+// Coordinate update of block l-1 and the RBF embedding of block l in ONE per-molecule kernel (dmt.py:53-58 + 136-138):
+// CTA = molecule (largest first).  The directed-edge weights and the positions of the molecule are staged in shared
+// memory with coalesced loads, threads r < n apply pos_r += sum_c (pos_r - pos_c)/|.| * scale * w[r,c] and remove the
+// centre of mass, the new positions go back to HBM (fp32 stream) and stay in shared memory, from which the same CTA
+// writes X[:, 0:64] of the molecule's pairs (8 threads per pair, 8 channels each, per-channel constants in registers).
+// do_update = 0 for block 0 (no coordinate update precedes it).
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256, 4) k_pos_rbf(Plan plan, int do_update, const float* __restrict__ wdir,
+                                                    const float* __restrict__ scale_p, float* __restrict__ pos,
+                                                    const float* __restrict__ ada, int l, const float* __restrict__ means,
+                                                    const float* __restrict__ stds, AT* __restrict__ X) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sw[MAX_ATOMS * (MAX_ATOMS - 1)];
+  __shared__ float sp[MAX_ATOMS][3];
+  __shared__ float red[3][2];
+  const int mol = plan.mol_order[blockIdx.x], t = threadIdx.x;
+  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
+  const int np = n * (n - 1) / 2;
+  // issued before the position phase so that their latency overlaps it
+  const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_RBF;
+  const float a_scale = ar[0] + 1.0f, a_shift = ar[1];
+  const int k0 = (t & 7) * 8;
+  float mean[8], sd[8], coef[8];     // fast mode: sd / coef hold the RECIPROCALS
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int kk = k0 + k;
+    mean[k] = kk ? means[kk - 1] : 0.f;
+    sd[k] = kk ? fabsf(stds[kk - 1]) + 1e-5f : 1.f;
+    coef[k] = 2.5066272160016134f * sd[k];       // (2*3.14159)**0.5 * std
+    if (kFast) { sd[k] = __fdividef(1.0f, sd[k]); coef[k] = __fdividef(1.0f, coef[k]); }
+  }
+  if (do_update) {
+    const float* wsrc = wdir + static_cast<size_t>(2) * pbase;
+    for (int idx = t; idx < 2 * np; idx += 256) sw[idx] = wsrc[idx];
+  }
+  if (t < n * 3) (&sp[0][0])[t] = pos[static_cast<size_t>(base) * 3 + t];
+  __syncthreads();
+  if (do_update) {
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (t < 64) {
+      const int r = t;
+      if (r < n) {
+        const float scale = scale_p[0];
+        const float px = sp[r][0], py = sp[r][1], pz = sp[r][2];
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        const float* wr = sw + r * (n - 1);
+        for (int c = 0; c < n; ++c) {
+          if (c == r) continue;
+          const float dx = px - sp[c][0], dy = py - sp[c][1], dz = pz - sp[c][2];
+          const float w = wr[c - (c > r ? 1 : 0)];
+          if (kFast) {
+            const float f = rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-16f)) * scale * w;
+            ax = fmaf(dx, f, ax);
+            ay = fmaf(dy, f, ay);
+            az = fmaf(dz, f, az);
+          } else {
+            const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
+            ax += (dx / nrm * scale) * w;
+            ay += (dy / nrm * scale) * w;
+            az += (dz / nrm * scale) * w;
+          }
+        }
+        nx = px + ax; ny = py + ay; nz = pz + az;
+      }
+      const float sx = warp_sum(nx), sy = warp_sum(ny), sz = warp_sum(nz);
+      if ((r & 31) == 0) { red[0][r >> 5] = sx; red[1][r >> 5] = sy; red[2][r >> 5] = sz; }
+    }
+    __syncthreads();          // every thread has read sp (old positions) and red is complete
+    if (t < n) {
+      const float fn = static_cast<float>(n);
+      nx -= (red[0][0] + red[0][1]) / fn;
+      ny -= (red[1][0] + red[1][1]) / fn;
+      nz -= (red[2][0] + red[2][1]) / fn;
+      sp[t][0] = nx; sp[t][1] = ny; sp[t][2] = nz;
+      pos[(base + t) * 3 + 0] = nx;
+      pos[(base + t) * 3 + 1] = ny;
+      pos[(base + t) * 3 + 2] = nz;
+    }
+    __syncthreads();
+  }
+  // RBF of the molecule's pairs from the shared-memory positions
+  for (int q0 = 0; q0 < np; q0 += 64) {
+    int qq[2];
+    uint32_t info[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      qq[u] = q0 + u * 32 + (t >> 3);
+      info[u] = __ldg(plan.pair_info + pbase + min(qq[u], np - 1));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (qq[u] >= np) break;
+      const int i = (info[u] >> 6) & 63, j = info[u] & 63;
+      const float dx = sp[i][0] - sp[j][0], dy = sp[i][1] - sp[j][1], dz = sp[i][2] - sp[j][2];
+      const float r2 = dx * dx + dy * dy + dz * dz;
+      const float x = r2 * a_scale + a_shift;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (kFast) {
+          const float tt = (x - mean[k]) * sd[k];
+          v[k] = ex2_approx(-0.72134752044448170368f * (tt * tt)) * coef[k];     // exp(-0.5 t^2) = 2^(-0.5 log2(e) t^2)
+        } else {
+          const float tt = (x - mean[k]) / sd[k];
+          v[k] = expf(-0.5f * (tt * tt)) / coef[k];
+        }
+      }
+      if (k0 == 0) v[0] = x;
+      AT* o = X + static_cast<size_t>(pbase + qq[u]) * 128 + k0;
+      store4<AT>(o, v[0], v[1], v[2], v[3]);
+      store4<AT>(o + 4, v[4], v[5], v[6], v[7]);
+    }
   }
 }
 
@@ -1100,6 +1221,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     return DS_OK;
   };
 
+  const bool pos_rbf = (ctx->fuse_mask & 128) && Mp > 0;
   for (int l = 0; l < N_LAYERS; ++l) {
     const BlockWeights& bw = pw.blk[l];
     const float* ada_l = w.ada + l * ADA_BLK;
@@ -1107,7 +1229,11 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     // ---- pair chain A: RBF -> edge_emb + LN + modulate -> lin_edge0 | lin_edge1
     ctx->cta_cap = ecap;
     if (Mp > 0) {
-      ds_launch(k_rbf<AT, kFast>, dim3(cdiv(Mp, 128)), dim3(256), 0, se, plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
+      if (pos_rbf)
+        ds_launch(k_pos_rbf<AT, kFast>, dim3(B), dim3(256), 0, se, plan, l > 0 ? 1 : 0, w.wdir, l > 0 ? pw.blk[l - 1].coord_scale : bw.coord_scale,
+                  w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
+      else
+        ds_launch(k_rbf<AT, kFast>, dim3(cdiv(Mp, 128)), dim3(256), 0, se, plan, w.pos, w.ada, l, bw.rbf_means, bw.rbf_stds, X);
       LAUNCH_CHECK(ctx);
       if (kFast && (ctx->fuse_mask & 1)) {
         // edge_emb -> LayerNorm -> modulate fused in the GEMM epilogue
@@ -1215,7 +1341,8 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         }
       }
     }
-    ds_launch(k_pos_update<kFast>, dim3(B), dim3(128), 0, s, plan, w.wdir, bw.coord_scale, w.pos);
+    if (!pos_rbf || l == N_LAYERS - 1)     // otherwise applied by the next block's k_pos_rbf
+      ds_launch(k_pos_update<kFast>, dim3(B), dim3(128), 0, s, plan, w.wdir, bw.coord_scale, w.pos);
     LAUNCH_CHECK(ctx);
   }
 

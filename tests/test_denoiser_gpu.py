@@ -131,7 +131,7 @@ def test_weights_changed_through_data_copy_are_repacked():
     right = build_model('ir', g['salt'], g['coord_scale'], 'fp32', device='cpu').state_dict()
     key = model._params_key()
     with torch.no_grad():
-        for (n, p) in model.named_parameters():                              # what ema.copy_to does
+        for (n, p) in list(model.named_parameters()) + list(model.named_buffers()):   # what ema.copy_to does
             p.data.copy_(right[n].data)
     assert model._params_key() == key                                        # the cheap key is blind to it
     pred, epred, c = _run_case(model, g, 'step0')                            # fresh context tensors = new round

@@ -245,3 +245,19 @@ def test_eval_driver_contract_and_rank_sharding():
         assert a[0].shape == b[0].shape
         same += int(torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and (a[0] - b[0]).abs().max() < 1e-3)
     assert same >= n_samples - 1        # identical noise per global molecule id; bf16 tiles cut differently
+
+
+def test_sharded_eval_driver_single_process():
+    """diffspectra_b200.evaluate at world_size 1: same result lists as the local driver.  The
+    2-GPU NCCL path is exercised by tests/run_eval_sharded.py under torchrun."""
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.join(root, 'tests', 'run_eval_sharded.py')], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert 'EVAL_SHARDED world=1 samples=53' in out.stdout and 'OK' in out.stdout
