@@ -915,15 +915,18 @@ __global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* _
   const int mol = info >> 6, r = info & 63;
   const int n = plan.n_atoms[mol], pbase = plan.poff[mol];
   const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_COORD;
-  float a[8], sh[8], sc[8];
+  float2 a2[4], sh2[4], sc2[4];      // channel pairs: the fp32 arithmetic below is packed (FADD2 / FFMA2)
   {
+    float a[8];
     uint4 u = *reinterpret_cast<const uint4*>(ab + static_cast<size_t>(m) * 512 + 8 * lane);
     unpack8c(u, a);
     const float4 s0 = *reinterpret_cast<const float4*>(ar + 8 * lane), s1 = *reinterpret_cast<const float4*>(ar + 8 * lane + 4);
     const float4 c0 = *reinterpret_cast<const float4*>(ar + 256 + 8 * lane), c1 = *reinterpret_cast<const float4*>(ar + 256 + 8 * lane + 4);
-    sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
-    sc[0] = 1.f + c0.x; sc[1] = 1.f + c0.y; sc[2] = 1.f + c0.z; sc[3] = 1.f + c0.w;
-    sc[4] = 1.f + c1.x; sc[5] = 1.f + c1.y; sc[6] = 1.f + c1.z; sc[7] = 1.f + c1.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a2[k] = make_float2(a[2 * k], a[2 * k + 1]);
+    sh2[0] = make_float2(s0.x, s0.y); sh2[1] = make_float2(s0.z, s0.w); sh2[2] = make_float2(s1.x, s1.y); sh2[3] = make_float2(s1.z, s1.w);
+    sc2[0] = make_float2(1.f + c0.x, 1.f + c0.y); sc2[1] = make_float2(1.f + c0.z, 1.f + c0.w);
+    sc2[2] = make_float2(1.f + c1.x, 1.f + c1.y); sc2[3] = make_float2(1.f + c1.z, 1.f + c1.w);
   }
   const size_t d0 = static_cast<size_t>(2 * pbase) + static_cast<size_t>(r) * (n - 1);
   const int4* di = plan.dir_info + d0;       // x = pair row, z = atom row of the target (plan table, no index arithmetic)
@@ -952,24 +955,28 @@ __global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* _
     issue(cc + kCoordDepth);                 // the slot just read is free again (this lane only touches its own 16 bytes)
     float v[8];
     unpack8c(bg, v);
-    float s = 0.f, q = 0.f;
+    float2 vp[4], sq = make_float2(0.f, 0.f), qq = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      v[k] += a[k];
-      s += v[k];
-      q = fmaf(v[k], v[k], q);
+    for (int k = 0; k < 4; ++k) {
+      vp[k] = fadd2(make_float2(v[2 * k], v[2 * k + 1]), a2[k]);
+      sq = fadd2(sq, vp[k]);
+      qq = ffma2(vp[k], vp[k], qq);
     }
-    // both reductions in flight together; var = E[y^2] - mean^2 in fp32 (|y| = O(1))
+    // both reductions travel together as one packed value; var = E[y^2] - mean^2 in fp32 (|y| = O(1))
+    float2 red = make_float2(sq.x + sq.y, qq.x + qq.y);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    const float mean = s * (1.0f / 256.0f);
-    const float is = rsqrtf(fmaxf(q * (1.0f / 256.0f) - mean * mean, 0.f) + kLnEps);
+    for (int o = 16; o > 0; o >>= 1)
+      red = fadd2(red, make_float2(__shfl_xor_sync(0xffffffffu, red.x, o), __shfl_xor_sync(0xffffffffu, red.y, o)));
+    const float mean = red.x * (1.0f / 256.0f);
+    const float is = rsqrtf(fmaxf(red.y * (1.0f / 256.0f) - mean * mean, 0.f) + kLnEps);
     const float nm = -mean * is;
+    const float2 is2 = make_float2(is, is), nm2 = make_float2(nm, nm);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], is, nm) * sc[k] + sh[k];
+    for (int k = 0; k < 4; ++k) {
+      const float2 t = ffma2(ffma2(vp[k], is2, nm2), sc2[k], sh2[k]);
+      v[2 * k] = t.x;
+      v[2 * k + 1] = t.y;
+    }
     uint4 o;
     o.x = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[0], v[1]));
     o.y = *reinterpret_cast<const uint32_t*>(&(const __nv_bfloat162&)__floats2bfloat162_rn(v[2], v[3]));

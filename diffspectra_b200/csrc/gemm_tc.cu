@@ -204,9 +204,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 9) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
   if constexpr (MODE == GEMM_COORD) {
-    if (threadIdx.x < 256)
-      swc2[threadIdx.x] = make_float4(ep.wc2[threadIdx.x], ep.wc2[256 + threadIdx.x], ep.wc2[512 + threadIdx.x],
-                                      ep.bias[threadIdx.x]);
+    if (threadIdx.x < 256) {     // per column PAIR (2p, 2p+1): [2p] = (w0, w0', w1, w1'), [2p+1] = (w2, w2', bias, bias')
+      const int c2 = threadIdx.x & ~1;
+      swc2[threadIdx.x] = (threadIdx.x & 1) ? make_float4(ep.wc2[512 + c2], ep.wc2[513 + c2], ep.bias[c2], ep.bias[c2 + 1])
+                                            : make_float4(ep.wc2[c2], ep.wc2[c2 + 1], ep.wc2[256 + c2], ep.wc2[257 + c2]);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -425,21 +427,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (row_ok) *reinterpret_cast<float2*>(ep.wdir + static_cast<size_t>(row) * 2) = make_float2(s0, s1);
       } else {   // GEMM_COORD, BN == N == 256
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        // two columns per step as packed fp32 (FADD2 + 4 FFMA2 + 2 MUFU per pair instead of 2 FADD + 8 FFMA + 2 MUFU):
+        // even / odd columns accumulate separately and meet at the end
+        float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0;
         const int c_lo = second ? 128 : 0;
 #pragma unroll 1
         for (int c = c_lo; c < c_lo + 128; c += 32) {
           float f[32];
           load_acc<32>(t_addr + c, f);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float4 w = swc2[c + i];
-            const float v = act_silu_half<true>(f[i] + w.w);      // coord_mlp.0 is packed with 0.5 W, 0.5 b
-            s0 = fmaf(v, w.x, s0);
-            s1 = fmaf(v, w.y, s1);
-            s2 = fmaf(v, w.z, s2);
+          for (int i = 0; i < 32; i += 2) {
+            const float4 wa = swc2[c + i], wb = swc2[c + i + 1];
+            const float2 h = fadd2(make_float2(f[i], f[i + 1]), make_float2(wb.z, wb.w));   // coord_mlp.0 is packed with 0.5 W, 0.5 b
+            const float2 v = ffma2(h, make_float2(act_tanh<true>(h.x), act_tanh<true>(h.y)), h);   // SiLU(2h) = h + h tanh(h)
+            p0 = ffma2(v, make_float2(wa.x, wa.y), p0);
+            p1 = ffma2(v, make_float2(wa.z, wa.w), p1);
+            p2 = ffma2(v, make_float2(wb.x, wb.y), p2);
           }
         }
+        float s0 = p0.x + p0.y, s1 = p1.x + p1.y, s2 = p2.x + p2.y;
         float4* sp = spart + g * 128 + wq * 32 + lane;
         if (second) *sp = make_float4(s0, s1, s2, 0.f);
         named_bar_sync(3 + g, 256);                     // the two warps of every row have met
