@@ -97,6 +97,13 @@ constexpr int N_SUB = N_HEADS - N_XHEADS;   // 14 learned heads
 constexpr int C_SUB = 18;                   // 256 / 14
 constexpr int C_HEAD = 16;
 constexpr int QK_DIM = N_SUB * C_SUB;       // 252
+// Column order of q, k (inside qkv) and e0 (inside e01): channel d of head h lives at head_perm(h * C_SUB + d), i.e. the 14
+// heads' channel PAIRS are interleaved ([d/2][h][d%2]).  The logits are sums over channels of q*k*e0 per head, so any
+// common permutation is exact; this one makes the 14 lanes that work on one (source, target) pair read 56 contiguous
+// bytes per load instead of 14 words 36 bytes apart (2 sectors instead of 16 through L1 per request).  Applied once,
+// to the rows of lin_query / lin_key / lin_edge0 (and the biases), when the weights are packed.
+__host__ __device__ constexpr int head_perm(int c) { return (((c % C_SUB) >> 1) * N_SUB + c / C_SUB) * 2 + (c & 1); }
+constexpr int QK_PAIR_STRIDE = 2 * N_SUB;   // 28 elements between consecutive channel pairs of one head
 constexpr int QKV_LD = 768;                 // q[0,252) pad, k[256,508) pad, v[512,768)
 constexpr int E01_LD = 512;                 // e0[0,252) pad, e1[256,512)
 constexpr int MAX_ATOMS = 64;               // stress config; QM9S has <= 29

@@ -598,9 +598,11 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
     const int row = srow[jl][i];
     if (row < 0) continue;
     if (hh < N_SUB) {
-      const AT* er = e01 + static_cast<size_t>(row) * E01_LD + hh * C_SUB;
-      const AT* kr = qkv + static_cast<size_t>(base + i) * QKV_LD + 256 + hh * C_SUB;
-      const float* qr = &sq[jl][hh * C_SUB];
+      // head-interleaved channel order (common.cuh: head_perm): pair d of head hh sits at d * 28 + hh * 2, so the 14 lanes
+      // of one (source, target) pair read 56 contiguous bytes per request
+      const AT* er = e01 + static_cast<size_t>(row) * E01_LD + hh * 2;
+      const AT* kr = qkv + static_cast<size_t>(base + i) * QKV_LD + 256 + hh * 2;
+      const float* qr = &sq[jl][hh * 2];
       float a = 0.f;
       if constexpr (sizeof(AT) == 2) {
         // all 18 loads of the row pair are issued before the first use (memory-level parallelism), then
@@ -608,12 +610,12 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
         __nv_bfloat162 ev[C_SUB / 2], kv[C_SUB / 2];
 #pragma unroll
         for (int d = 0; d < C_SUB / 2; ++d) {
-          ev[d] = *reinterpret_cast<const __nv_bfloat162*>(er + 2 * d);
-          kv[d] = *reinterpret_cast<const __nv_bfloat162*>(kr + 2 * d);
+          ev[d] = *reinterpret_cast<const __nv_bfloat162*>(er + QK_PAIR_STRIDE * d);
+          kv[d] = *reinterpret_cast<const __nv_bfloat162*>(kr + QK_PAIR_STRIDE * d);
         }
 #pragma unroll
         for (int d = 0; d < C_SUB / 2; ++d) {
-          const float2 qv = *reinterpret_cast<const float2*>(qr + 2 * d);
+          const float2 qv = *reinterpret_cast<const float2*>(qr + QK_PAIR_STRIDE * d);
           const float2 ke = bf2_to_f2(__hmul2(ev[d], kv[d]));
           a = fmaf(qv.x, ke.x, a);
           a = fmaf(qv.y, ke.y, a);
@@ -621,9 +623,9 @@ __global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, c
       } else {
 #pragma unroll
         for (int d = 0; d < C_SUB; d += 2) {
-          const float2 qv = *reinterpret_cast<const float2*>(qr + d);
-          const float2 ev = ld_pair2(er + d);
-          const float2 kv = ld_pair2(kr + d);
+          const float2 qv = *reinterpret_cast<const float2*>(qr + (QK_PAIR_STRIDE / 2) * d);
+          const float2 ev = ld_pair2(er + (QK_PAIR_STRIDE / 2) * d);
+          const float2 kv = ld_pair2(kr + (QK_PAIR_STRIDE / 2) * d);
           a = fmaf(qv.x * kv.x, ev.x, a);
           a = fmaf(qv.y * kv.y, ev.y, a);
         }

@@ -23,6 +23,20 @@ __global__ void k_transpose(const float* __restrict__ src, float* __restrict__ d
   dst[static_cast<size_t>(c) * rows + r] = src[idx];
 }
 
+// dst row head_perm(r) <- src row r  (matrix [QK_DIM, cols]);  vec: dst[head_perm(c)] <- src[c]
+template <typename T>
+__global__ void k_copy_headperm(const float* __restrict__ src, int src_ld, T* __restrict__ dst, int dst_ld, int rows, int cols,
+                                int vec) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int r = idx / cols, c = idx % cols;
+  const float v = src[static_cast<size_t>(r) * src_ld + c];
+  if (vec)
+    dst[head_perm(c)] = from_f32<T>(v);
+  else
+    dst[static_cast<size_t>(head_perm(r)) * dst_ld + c] = from_f32<T>(v);
+}
+
 struct Packer {
   DsContext* ctx;
   std::map<std::string, const float*> params;
@@ -55,6 +69,15 @@ struct Packer {
       k_copy2d<bf16><<<(n + 255) / 256, 256, 0, s>>>(src, src_ld, static_cast<bf16*>(dst) + dst_off, dst_ld, rows, cols, scale);
     else
       k_copy2d<float><<<(n + 255) / 256, 256, 0, s>>>(src, src_ld, static_cast<float*>(dst) + dst_off, dst_ld, rows, cols, scale);
+  }
+  // the head-interleaved order of q / k / e0 (common.cuh: head_perm): [QK_DIM, cols] weight rows, or a QK_DIM bias vector
+  void copy_headperm(const float* src, int src_ld, void* dst, size_t dst_off, int dst_ld, int cols, bool act, bool vec) {
+    if (arena.dry || err != DS_OK || src == nullptr || dst == nullptr) return;
+    const int rows = vec ? 1 : QK_DIM, cc = vec ? QK_DIM : cols, n = rows * cc;
+    if (act && bf)
+      k_copy_headperm<bf16><<<(n + 255) / 256, 256, 0, s>>>(src, src_ld, static_cast<bf16*>(dst) + dst_off, dst_ld, rows, cc, vec ? 1 : 0);
+    else
+      k_copy_headperm<float><<<(n + 255) / 256, 256, 0, s>>>(src, src_ld, static_cast<float*>(dst) + dst_off, dst_ld, rows, cc, vec ? 1 : 0);
   }
   // whole matrix [rows, cols] in the act dtype
   const void* mat(const std::string& name, int rows, int cols, float scale = 1.0f) {
@@ -160,16 +183,16 @@ int build(Packer& P, PackedWeights& pw) {
     b.edge_emb_w = P.mat(p + "edge_emb.weight", 64, 128);
     b.edge_emb_b = P.vec(p + "edge_emb.bias", 64);
     void* w01 = P.alloc_act(static_cast<size_t>(E01_LD) * 64);
-    P.copy(P.get(p + "attn_mpnn.lin_edge0.weight"), 64, w01, 0, 64, QK_DIM, 64, true);
+    P.copy_headperm(P.get(p + "attn_mpnn.lin_edge0.weight"), 64, w01, 0, 64, 64, true, false);
     P.copy(P.get(p + "attn_mpnn.lin_edge1.weight"), 64, w01, 256 * 64, 64, 256, 64, true);
     b.w01 = w01;
     void* wqkv = P.alloc_act(static_cast<size_t>(QKV_LD) * 256);
     float* bqkv = P.alloc_f32(QKV_LD);
-    P.copy(P.get(p + "attn_mpnn.lin_query.weight"), 256, wqkv, 0, 256, QK_DIM, 256, true);
-    P.copy(P.get(p + "attn_mpnn.lin_key.weight"), 256, wqkv, 256 * 256, 256, QK_DIM, 256, true);
+    P.copy_headperm(P.get(p + "attn_mpnn.lin_query.weight"), 256, wqkv, 0, 256, 256, true, false);
+    P.copy_headperm(P.get(p + "attn_mpnn.lin_key.weight"), 256, wqkv, 256 * 256, 256, 256, true, false);
     P.copy(P.get(p + "attn_mpnn.lin_value.weight"), 256, wqkv, 512 * 256, 256, 256, 256, true);
-    P.copy(P.get(p + "attn_mpnn.lin_query.bias"), QK_DIM, bqkv, 0, QK_DIM, 1, QK_DIM, false);
-    P.copy(P.get(p + "attn_mpnn.lin_key.bias"), QK_DIM, bqkv, 256, QK_DIM, 1, QK_DIM, false);
+    P.copy_headperm(P.get(p + "attn_mpnn.lin_query.bias"), QK_DIM, bqkv, 0, QK_DIM, QK_DIM, false, true);
+    P.copy_headperm(P.get(p + "attn_mpnn.lin_key.bias"), QK_DIM, bqkv, 256, QK_DIM, QK_DIM, false, true);
     P.copy(P.get(p + "attn_mpnn.lin_value.bias"), 256, bqkv, 512, 256, 1, 256, false);
     b.wqkv = wqkv;
     b.bqkv = bqkv;
