@@ -84,7 +84,8 @@ def test_noise_kat_vs_reference_golden():
 
 
 @pytest.mark.parametrize('name,use_graph', [('sampler_ir_50.pt', True), ('sampler_ir_50.pt', False),
-                                            ('sampler_allspectra_20.pt', True)])
+                                            ('sampler_allspectra_20.pt', True),
+                                            ('sampler_allspectra_1000.pt', True)])     # the shipped length: 1000 steps
 def test_free_running_sampling_matches_reference_golden(name, use_graph):
     """Whole loop, fp32 mode, the reference's own RNG stream (torch.manual_seed(42) + its draw order):
     final argmax atom types / bond orders identical, coordinate RMSD <= 1e-3 A (north_star)."""
