@@ -1350,9 +1350,10 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         }
       }
     }
-    if (!pos_rbf || l == N_LAYERS - 1)     // otherwise applied by the next block's k_pos_rbf
+    if (!pos_rbf || l == N_LAYERS - 1) {   // otherwise applied by the next block's k_pos_rbf
       ds_launch(k_pos_update<kFast>, dim3(B), dim3(128), 0, s, plan, w.wdir, bw.coord_scale, w.pos);
-    LAUNCH_CHECK(ctx);
+      LAUNCH_CHECK(ctx);
+    }
   }
 
   // prediction heads (dmt.py:391-399)
