@@ -133,3 +133,24 @@ def test_restore_checkpoint_and_ema_copy_to_through_reference_code(tmp_path, kin
     # see it, the content fingerprint checked at the start of every sampling round does
     assert ours.module._params_key() == key_before
     assert not torch.equal(ours.module._fingerprint(), fp_before)
+
+
+@needs_ref
+def test_create_model_resolves_the_b200_names_through_the_reference_registry():
+    """models/utils.py:5-28: `create_model(config)` = `_MODELS[config.model.name](config).to(device)` in a DataParallel;
+    `diffspectra_b200.model.register()` is the only hook needed for `--config.model.name DMT_B200 | DMT_WO_EQ_B200`."""
+    from diffspectra_b200 import model as M
+    ref = ref_harness.load_reference()
+    M.register(ref.mutils)
+    M.register(ref.mutils)                                   # idempotent
+    cfg = ref.config
+    cfg.data.spectra_version = 'allspectra'
+    cfg.model.pretrained_specformer_path = ''
+    for name, cls, ref_cls in (('DMT_B200', M.DMT_B200, ref.DMT), ('DMT_WO_EQ_B200', M.DMT_WO_EQ_B200, ref.DMT_WO_EQ)):
+        cfg.model.name = name
+        m = ref.mutils.create_model(cfg)
+        assert isinstance(m, torch.nn.DataParallel) and isinstance(m.module, cls)
+        # same parameter inventory as the reference class built from the same config object (EMA order)
+        cfg.model.name = ref_cls.__name__
+        r = ref.mutils.create_model(cfg)
+        assert [(n, tuple(p.shape)) for n, p in m.named_parameters()] == [(n, tuple(p.shape)) for n, p in r.named_parameters()]
