@@ -188,14 +188,24 @@ def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if rank == 0:
         B.build()
     if world > 1:
-        dist.barrier()
+        # NCCL prints its version banner on stdout at communicator creation when NCCL_DEBUG=VERSION is set in the
+        # environment; stdout carries exactly ONE JSON line, so the banner goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     Bsz, S, N_PAD = args.batch, args.diffusion_steps, args.n_pad
     torch.manual_seed(42)                                   # random-init weights of the reference architecture

@@ -561,38 +561,38 @@ __device__ __forceinline__ uint4 ldg128_pinned(const void* p) {
   return v;
 }
 __device__ __forceinline__ float2 ld_pair2(const float* p) { return *reinterpret_cast<const float2*>(p); }
-template <typename AT, bool kFast, int MAXN>
-__global__ void __launch_bounds__(256, 6) k_attention_grp(Plan plan, int ngrp, const AT* __restrict__ qkv,
+template <typename AT, bool kFast, int MAXN, int G>
+__global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int ngrp, const AT* __restrict__ qkv,
                                                        const AT* __restrict__ e01, const uint8_t* __restrict__ pflags,
                                                        float* __restrict__ hn, AT* __restrict__ hnb) {
   pdl_trigger();
   pdl_wait();
-  __shared__ __align__(16) float sq[ATT_G][256];
+  __shared__ __align__(16) float sq[G][256];
   // logits / softmax weights: fp32 in validation mode; fp16 in production mode (|logit| = O(1), weights in [0,1]) so that
   // six CTAs leave ~120 KB of the SM's 228 KB to L1, which serves the k / v rows and the second read of every pair row
   typedef typename std::conditional<kFast, __half, float>::type LT;
-  __shared__ LT slog[ATT_G][MAXN][N_HEADS];
-  __shared__ int srow[ATT_G][MAXN];
-  __shared__ float sinv[ATT_G][N_HEADS];             // 1 / softmax denominator, applied once to the accumulated messages
+  __shared__ LT slog[G][MAXN][N_HEADS];
+  __shared__ int srow[G][MAXN];
+  __shared__ float sinv[G][N_HEADS];             // 1 / softmax denominator, applied once to the accumulated messages
   // CTAs are issued largest molecule first (plan.mol_order), so the kernel's tail is made of its cheapest CTAs
-  const int mol = plan.mol_order[blockIdx.x / ngrp], j0 = (blockIdx.x % ngrp) * ATT_G;
+  const int mol = plan.mol_order[blockIdx.x / ngrp], j0 = (blockIdx.x % ngrp) * G;
   const int n = plan.n_atoms[mol];
   if (j0 >= n) return;
   const int t = threadIdx.x;
   const int base = plan.noff[mol], pbase = plan.poff[mol];
-  const int gsz = min(ATT_G, n - j0);
-  for (int idx = t; idx < gsz * 64; idx += 256) {     // q rows of the targets (252 values, padded to 256)
+  const int gsz = min(G, n - j0);
+  for (int idx = t; idx < gsz * 64; idx += 32 * G) {     // q rows of the targets (252 values, padded to 256)
     const int jl = idx >> 6, c4 = idx & 63;
     *reinterpret_cast<float4*>(&sq[jl][c4 * 4]) = load4<AT>(qkv + static_cast<size_t>(base + j0 + jl) * QKV_LD + c4 * 4);
   }
-  for (int idx = t; idx < gsz * n; idx += 256) {
+  for (int idx = t; idx < gsz * n; idx += 32 * G) {
     const int jl = idx / n, i = idx - jl * n, j = j0 + jl;
     srow[jl][i] = (i == j) ? -1 : pbase + (i < j ? pair_index(n, i, j) : pair_index(n, j, i));
   }
   __syncthreads();
   // pass 1: logits[jl][i][h] for source i -> target j
   const unsigned rcp_n = 65536u / static_cast<unsigned>(n) + 1u;     // r / n == (r * rcp_n) >> 16 for r < 8 * 64
-  for (int idx = t; idx < gsz * n * N_HEADS; idx += 256) {
+  for (int idx = t; idx < gsz * n * N_HEADS; idx += 32 * G) {
     const int hh = idx & 15, r = idx >> 4;
     const int jl = static_cast<int>((static_cast<unsigned>(r) * rcp_n) >> 16), i = r - jl * n;
     const int row = srow[jl][i];
@@ -1264,12 +1264,24 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hh, 256, bw.wqkv, 256, bw.bqkv, nullptr, 0, w.qkv, QKV_LD, AD, Mn, QKV_LD, 256, ACT_NONE, sn));
     DS_TRY(join());
-    if (plan.N <= 32)
-      ds_launch(k_attention_grp<AT, kFast, 32>, dim3(B * ngrp), dim3(256), 0, s, plan, ngrp, reinterpret_cast<const AT*>(w.qkv), reinterpret_cast<const AT*>(w.e01), w.pflags,
-                                                              w.hn, reinterpret_cast<AT*>(w.hnb));
-    else
-      ds_launch(k_attention_grp<AT, kFast, 64>, dim3(B * ngrp), dim3(256), 0, s, plan, ngrp, reinterpret_cast<const AT*>(w.qkv), reinterpret_cast<const AT*>(w.e01), w.pflags,
-                                                              w.hn, reinterpret_cast<AT*>(w.hnb));
+    {
+      const int ag = (kFast && ctx->att_g == 4) ? 4 : ATT_G;      // targets (= warps) per attention CTA
+      const int ngrp_a = (plan.N + ag - 1) / ag;
+      const AT* qkv_ = reinterpret_cast<const AT*>(w.qkv);
+      const AT* e01_ = reinterpret_cast<const AT*>(w.e01);
+      AT* hnb_ = reinterpret_cast<AT*>(w.hnb);
+      if (ag == 4) {
+        if (plan.N <= 32)
+          ds_launch(k_attention_grp<AT, kFast, 32, 4>, dim3(B * ngrp_a), dim3(128), 0, s, plan, ngrp_a, qkv_, e01_, w.pflags, w.hn, hnb_);
+        else
+          ds_launch(k_attention_grp<AT, kFast, 64, 4>, dim3(B * ngrp_a), dim3(128), 0, s, plan, ngrp_a, qkv_, e01_, w.pflags, w.hn, hnb_);
+      } else {
+        if (plan.N <= 32)
+          ds_launch(k_attention_grp<AT, kFast, 32, ATT_G>, dim3(B * ngrp), dim3(256), 0, s, plan, ngrp, qkv_, e01_, w.pflags, w.hn, hnb_);
+        else
+          ds_launch(k_attention_grp<AT, kFast, 64, ATT_G>, dim3(B * ngrp), dim3(256), 0, s, plan, ngrp, qkv_, e01_, w.pflags, w.hn, hnb_);
+      }
+    }
     LAUNCH_CHECK(ctx);
     DS_TRY(linear(ctx, w.hnb, 256, bw.n2e_w, 256, nullptr, nullptr, 0, w.pn, 64, DT_F32, Mn, 64, 256, ACT_NONE, s));
     DS_TRY(fork());
