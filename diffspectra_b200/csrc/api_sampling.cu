@@ -27,9 +27,9 @@ struct CtxFull : DsContext {
 inline CtxFull* full(ds_ctx* h) { return reinterpret_cast<CtxFull*>(h); }
 
 // plan blob layout (device, int32): n_atoms[B] | noff[B+1] | poff[B+1] | node_info[Mn_max] | pair_info[Mp_max] |
-// dir_info[2*Mp_max] (int4) | dir_mol[2*Mp_max] | pair_rows[Mp_max] (int2) | mol_order[B]
+// dir_info[2*Mp_max] (int4) | dir_mol[2*Mp_max] | pair_rows[Mp_max] (int2) | mol_order[B] | node_order[Mn_max]
 struct PlanLayout {
-  size_t n_atoms, noff, poff, node_info, pair_info, dir_info, dir_mol, pair_rows, mol_order, total;
+  size_t n_atoms, noff, poff, node_info, pair_info, dir_info, dir_mol, pair_rows, mol_order, node_order, total;
 };
 PlanLayout plan_layout(int B, int N) {
   PlanLayout L;
@@ -44,6 +44,7 @@ PlanLayout plan_layout(int B, int N) {
   L.dir_mol = o; o = al(o + size_t(B) * N * (N - 1) * 4 + 4);
   L.pair_rows = o; o = al(o + size_t(B) * N * (N - 1) / 2 * 8 + 8);
   L.mol_order = o; o = al(o + size_t(B) * 4);
+  L.node_order = o; o = al(o + size_t(B) * N * 4);
   L.total = o;
   return L;
 }
@@ -62,6 +63,7 @@ int make_plan(const void* plan_dev, int B, int N, int Mn, int Mp, Plan* p) {
   p->dir_mol = reinterpret_cast<const uint32_t*>(base + L.dir_mol);
   p->pair_rows = reinterpret_cast<const int2*>(base + L.pair_rows);
   p->mol_order = reinterpret_cast<const int*>(base + L.mol_order);
+  p->node_order = reinterpret_cast<const int*>(base + L.node_order);
   return DS_OK;
 }
 
@@ -157,6 +159,11 @@ int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_d
     for (int b = 0; b < B; ++b) idx[b] = b;
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return na[a] > na[b]; });
     for (int b = 0; b < B; ++b) ord[b] = idx[b];
+    // the same order atom by atom, for the kernels whose warps map to atoms
+    int* nord = reinterpret_cast<int*>(host.data() + L.node_order);
+    int q = 0;
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < na[idx[b]]; ++i) nord[q++] = noff[idx[b]] + i;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   DS_CUDA_CHECK(cudaMemcpyAsync(plan_dev, host.data(), L.total, cudaMemcpyHostToDevice, s));

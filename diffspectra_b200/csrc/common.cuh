@@ -230,6 +230,7 @@ struct Plan {
   const uint32_t* dir_mol;     // [2*Mp] molecule of each directed edge (row_info form for the GEMM epilogues)
   const int2* pair_rows;       // [Mp] atom rows (i, j) of each unordered pair
   const int* mol_order;        // [B] molecules by descending atom count (launch order of the per-molecule kernels)
+  const int* node_order;       // [Mn] atom rows in that molecule order (launch order of the warp-per-atom kernels)
 };
 __device__ __forceinline__ int pair_index(int n, int i, int j) {   // i < j < n, row-major upper triangle
   return i * n - (i * (i + 1)) / 2 + (j - i - 1);

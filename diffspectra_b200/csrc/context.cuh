@@ -22,7 +22,7 @@ struct DsContext {
   int overlap = 0;                   // measured on B200: 455.9 ms / 100 steps without, 462-724 ms with (split 100,48 .. 140,8): the atom chain is
                                      // throughput-, not latency-bound, so a branch only takes SMs away from the pair chain
   int edge_cap = 124, node_cap = 24;
-  int att_g = 4;                     // DS_ATT_G: targets (= warps) per attention CTA; 4 -> 128-thread CTAs, 12 per SM: 82.1 us vs 84.4 us with 8 (finer tail)
+  int att_g = 4;                     // DS_ATT_G: targets (= warps) per attention CTA; 4 -> 128-thread CTAs, 12 per SM: 82.1 us vs 84.4 us with 8 (finer tail); 2 targets / 64 threads measured 84.7 us
   int cta_cap = 0;                   // cap applied to the next persistent-GEMM launches (0 = all SMs)
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

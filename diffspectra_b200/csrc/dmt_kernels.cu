@@ -911,8 +911,9 @@ __global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* _
   pdl_wait();
   __shared__ __align__(16) uint4 ring[8][kCoordDepth][2][32];      // [warp][slot][B | G][lane]
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * 8 + wi;
-  if (m >= plan.Mn) return;
+  const int mi = blockIdx.x * 8 + wi;
+  if (mi >= plan.Mn) return;
+  const int m = plan.node_order[mi];         // atoms of the largest molecules first: the grid ends on its shortest warps
   const uint32_t info = plan.node_info[m];
   const int mol = info >> 6, r = info & 63;
   const int n = plan.n_atoms[mol], pbase = plan.poff[mol];
