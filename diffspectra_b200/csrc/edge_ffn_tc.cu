@@ -56,6 +56,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// kCoop: the pre-LayerNorm row x = e + eg1 * (P[i] + P[j] + b) is built while the tile is STAGED, by the threads that
+// own consecutive 16-byte chunks of a row (16 lanes read one 256-byte P row), instead of by the row's own thread (32
+// lanes reading 16 bytes each of 32 different P rows: 32 L1 wavefronts per load instruction, 32 such loads per thread).
+template <bool kCoop>
 __global__ void __launch_bounds__(kThreads, 1)
 edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmW4, EdgeFfnArgs a) {
   pdl_trigger();
@@ -172,7 +176,37 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
       const int2 rows = __ldg(a.pair_rows + pc);
       const float* ar = a.ada + static_cast<size_t>(__ldg(a.pair_info + pc) >> 12) * ADA_LD;
       // ---- 1. stage the tile's e rows: 2048 float4, coalesced, 16-byte chunks XOR-swizzled by the row
-      {
+      if constexpr (kCoop) {
+        const float4* src = reinterpret_cast<const float4*>(a.e + static_cast<size_t>(p0) * 64);
+        const int nrow = min(a.Mp - p0, TM);
+        const int ch = r & 15;                       // this thread's chunk of every row it touches
+        const float4 bn = *reinterpret_cast<const float4*>(sbn + ch * 4);
+#pragma unroll
+        for (int qb = 0; qb < 16; qb += 4) {         // four rows per batch: 16 independent 16-byte loads in flight
+          float4 te[4], tpi[4], tpj[4], tg[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int row = (qb + u) * 8 + (r >> 4);
+            const int prow = p0 + min(row, nrow - 1);
+            const int2 rr = __ldg(a.pair_rows + prow);
+            const float* arr = a.ada + static_cast<size_t>(__ldg(a.pair_info + prow) >> 12) * ADA_LD;
+            te[u] = row < nrow ? src[row * 16 + ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+            tpi[u] = ldg128f(a.pn + static_cast<size_t>(rr.x) * 64 + ch * 4);
+            tpj[u] = ldg128f(a.pn + static_cast<size_t>(rr.y) * 64 + ch * 4);
+            tg[u] = ldg128f(arr + 128 + ch * 4);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int row = (qb + u) * 8 + (r >> 4);
+            float4 x;
+            x.x = te[u].x + tg[u].x * ((tpi[u].x + tpj[u].x) + bn.x);
+            x.y = te[u].y + tg[u].y * ((tpi[u].y + tpj[u].y) + bn.y);
+            x.z = te[u].z + tg[u].z * ((tpi[u].z + tpj[u].z) + bn.z);
+            x.w = te[u].w + tg[u].w * ((tpi[u].w + tpj[u].w) + bn.w);
+            *reinterpret_cast<float4*>(buf + row * 256 + ((ch ^ (row & 15)) << 4)) = x;
+          }
+        }
+      } else {
         const float4* src = reinterpret_cast<const float4*>(a.e + static_cast<size_t>(p0) * 64);
         const int lim = (min(a.Mp - p0, TM)) * 16;
         float4 t[16];
@@ -191,6 +225,14 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
       // ---- 2. own row -> registers; residual sum, LayerNorm, modulate: all thread-local
       float v[64];
       float sum = 0.f;
+      if constexpr (kCoop) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float4 ev = *reinterpret_cast<const float4*>(buf + r * 256 + ((c ^ (r & 15)) << 4));
+          v[c * 4 + 0] = ev.x; v[c * 4 + 1] = ev.y; v[c * 4 + 2] = ev.z; v[c * 4 + 3] = ev.w;
+          sum += (ev.x + ev.y) + (ev.z + ev.w);
+        }
+      } else
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {             // two halves of 32 channels: 24 independent loads in flight each
         float4 pi[8], pj[8], g1[8];
@@ -329,6 +371,7 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
   }
 }
 
+
 }  // namespace
 
 int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ldx, const float* pn, const float* n2e_b,
@@ -337,7 +380,8 @@ int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ld
   DS_CHECK(plan.pair_rows != nullptr, DS_ERR_INVALID, "edge_ffn: plan has no pair-row table");
   static bool attr_set[64] = {};            // the attribute is per device: one flag per device ordinal
   if (!attr_set[ctx->device & 63]) {
-    DS_CUDA_CHECK(cudaFuncSetAttribute(edge_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    DS_CUDA_CHECK(cudaFuncSetAttribute(edge_ffn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    DS_CUDA_CHECK(cudaFuncSetAttribute(edge_ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set[ctx->device & 63] = true;
   }
   CUtensorMap tmW3, tmW4;
@@ -357,7 +401,11 @@ int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ld
   a.Mp = plan.Mp;
   const int tiles = (plan.Mp + TM - 1) / TM;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  ds_launch(edge_ffn_kernel, dim3(grid), dim3(kThreads), kSmem, s, tmW3, tmW4, a);
+  if (ctx->ffn_variant == 1) {
+    ds_launch(edge_ffn_kernel<true>, dim3(grid), dim3(kThreads), kSmem, s, tmW3, tmW4, a);
+  } else {
+    ds_launch(edge_ffn_kernel<false>, dim3(grid), dim3(kThreads), kSmem, s, tmW3, tmW4, a);
+  }
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;
   return DS_OK;
