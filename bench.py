@@ -328,8 +328,8 @@ def _demangle(name):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (MB) from the committed `ncu --set full` capture of this
-# command at batch 1024 / QM9S histogram (profiles/r1_final2_ncu.md); reported as roofline.traffic for the same workload only
-NCU_DRAM_MB = {'k_attention_grp': 213.1, 'k_coord_ln_async': 227.2, 'gemm_tc_kernel<256,COORD,0>': 172.1, 'edge_ffn_kernel': 68.0,
+# command at batch 1024 / QM9S histogram (profiles/r1_final3_ncu.md); reported as roofline.traffic for the same workload only
+NCU_DRAM_MB = {'k_attention_grp': 212.3, 'k_coord_ln_async': 227.7, 'gemm_tc_kernel<256,COORD,0>': 171.5, 'edge_ffn_kernel': 74.2,
                'gemm_tc_kernel<64,LNMOD,1>': 43.3, 'k_pos_rbf': 2.3}
 
 
@@ -413,7 +413,7 @@ def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
         'us_per_launch': top['us_per_launch'], 'share_of_step': top['share_of_step'],
         'what': 'dominant kernel of a denoiser step by in-stream CUDA-event time; achieved = algorithmic bytes (or FLOPs) per '
                 'launch / average launch time; peak = ' + peaks['which'] + ' (burst figures); traffic = ncu dram bytes per launch '
-                '(profiles/r1_final2_ncu.md), bytes',
+                '(profiles/r1_final3_ncu.md), bytes',
     }
     return {'dominant': dominant, 'kernels': rows[:14], 'step_us': total / steps}
 
