@@ -175,6 +175,10 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
       const int pc = ok ? p : a.Mp - 1;
       const int2 rows = __ldg(a.pair_rows + pc);
       const float* ar = a.ada + static_cast<size_t>(__ldg(a.pair_info + pc) >> 12) * ADA_LD;
+      if constexpr (kCoop) {     // shift | scale | gate2 of the row's molecule (768 bytes) are needed two and four steps from now
+#pragma unroll
+        for (int i = 0; i < 6; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(ar + 192 + i * 32));
+      }
       // ---- 1. stage the tile's e rows: 2048 float4, coalesced, 16-byte chunks XOR-swizzled by the row
       if constexpr (kCoop) {
         const float4* src = reinterpret_cast<const float4*>(a.e + static_cast<size_t>(p0) * 64);

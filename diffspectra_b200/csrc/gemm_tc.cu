@@ -283,6 +283,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = gtid; i < BN; i += 128) gb[i] = (ep.bias && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
         named_bar_sync(1 + g, 128);
       }
+      // the row's molecule and its adaLN vectors are known before the accumulator is: fetch the index and pull the
+      // lines into L1 now, so that the epilogue does not start with two dependent L2 round trips
+      uint32_t mol_pre = 0u;
+      if constexpr (MODE == GEMM_LNMOD || MODE == GEMM_RESGATE) {
+        const int row_pre = m0 + wq * 32 + lane;
+        if (row_pre < M && ep.row_info != nullptr && ep.ada != nullptr) {
+          mol_pre = ep.row_info[row_pre] >> ep.info_shift;
+          const float* ar = ep.ada + static_cast<size_t>(mol_pre) * ADA_LD;
+          constexpr int kLines = MODE == GEMM_LNMOD ? 2 : BN / 32;      // 128-byte lines of the first vector
+#pragma unroll
+          for (int i = 0; i < kLines; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(ar + ep.off_a + i * 32));
+          if constexpr (MODE == GEMM_LNMOD) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(ar + ep.off_b + i * 32));
+          }
+        }
+      }
       ptx::mbar_wait(&tfull_bar[g], gphase);
       ptx::tc_fence_after();
       const int row = m0 + wq * 32 + lane;
@@ -335,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 64; ++i) { f[i] -= mean; q += f[i] * f[i]; }
         const float is = rsqrtf(q * (1.0f / 64.0f) + 1e-6f);
-        const uint32_t mol = row_ok ? (ep.row_info[row] >> ep.info_shift) : 0u;
+        const uint32_t mol = mol_pre;
         const float* ar = ep.ada + static_cast<size_t>(mol) * ADA_LD;
 #pragma unroll
         for (int i = 0; i < 64; i += 4) {
@@ -362,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // fp32 stream and bf16 copy out via TMA stores; resid == null (tmR unused): plain acc + bias.
         const bool active = m0 + wq * 32 < M;
         const bool has_res = ep.resid != nullptr;
-        const uint32_t mol = (row_ok && has_res) ? (ep.row_info[row] >> ep.info_shift) : 0u;
+        const uint32_t mol = (row_ok && has_res) ? mol_pre : 0u;
         const float* gr = has_res ? ep.ada + static_cast<size_t>(mol) * ADA_LD + ep.off_a : nullptr;
         uint8_t* fbox = my_stage;                    // two fp32 boxes (cols 0-31, 32-63 of the chunk)
         uint8_t* bbox = my_stage + 2 * kStageBox;    // one bf16 box
