@@ -300,6 +300,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      uint8_t fl_pre = 0;
+      if constexpr (MODE == GEMM_COORD) {              // adjacency bits of the row: known now, needed at the very end
+        const int row_pre = m0 + wq * 32 + lane;
+        if (row_pre < M && warp < 8) fl_pre = ep.pflags[row_pre];
+      }
       ptx::mbar_wait(&tfull_bar[g], gphase);
       ptx::tc_fence_after();
       const int row = m0 + wq * 32 + lane;
@@ -471,7 +476,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           s0 += o.x; s1 += o.y; s2 += o.z;
         }
         if (row_ok && !second) {
-          const uint8_t fl = ep.pflags[row];            // per directed edge (k_coord_ln)
+          const uint8_t fl = fl_pre;                    // per directed edge (k_dir_flags), fetched before the accumulator wait
           const float a2 = (fl & 1) ? 1.f : 0.f, asp = (fl & 2) ? 1.f : 0.f;
           ep.wdir[row] = (act_tanh<true>(s0) + act_tanh<true>(s1) * a2 + act_tanh<true>(s2) * asp) / 3.0f;
         }
