@@ -165,7 +165,11 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(rates),
         'warmup': min(args.warmup, 1), 'ms_per_step': 1000.0 * args.batch / value, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args) + '; bounded sample', 'batch': args.batch, 'diffusion_steps': 1000},
+        # same workload keys as the CUDA arm's line; the CPU arm times a bounded sample of it (cpu_baseline.sample)
+        'config': {'workload': workload_name(args), 'model': args.model + ' (oracle port of the reference PyTorch path)',
+                   'batch_per_gpu': args.batch, 'diffusion_steps': args.diffusion_steps, 'n_pad': args.n_pad,
+                   'n_atoms': 'all %d' % args.n_pad if args.all_max else 'QM9S histogram', 'noise': 'torch generator',
+                   'sample': desc, 'parallelism': 'host threads: %d' % cores},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
