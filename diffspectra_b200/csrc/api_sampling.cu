@@ -27,9 +27,9 @@ struct CtxFull : DsContext {
 inline CtxFull* full(ds_ctx* h) { return reinterpret_cast<CtxFull*>(h); }
 
 // plan blob layout (device, int32): n_atoms[B] | noff[B+1] | poff[B+1] | node_info[Mn_max] | pair_info[Mp_max] |
-// dir_info[2*Mp_max] (int4) | dir_mol[2*Mp_max] | pair_rows[Mp_max] (int2) | mol_order[B] | node_order[Mn_max]
+// dir_info[2*Mp_max] (int4) | dir_mol[2*Mp_max] | pair_rows[Mp_max] (int2) | mol_order[B] | node_order[Mn_max] | mol_launch[B] (int4) | atom_launch[Mn_max] (int4)
 struct PlanLayout {
-  size_t n_atoms, noff, poff, node_info, pair_info, dir_info, dir_mol, pair_rows, mol_order, node_order, total;
+  size_t n_atoms, noff, poff, node_info, pair_info, dir_info, dir_mol, pair_rows, mol_order, node_order, mol_launch, atom_launch, total;
 };
 PlanLayout plan_layout(int B, int N) {
   PlanLayout L;
@@ -45,6 +45,8 @@ PlanLayout plan_layout(int B, int N) {
   L.pair_rows = o; o = al(o + size_t(B) * N * (N - 1) / 2 * 8 + 8);
   L.mol_order = o; o = al(o + size_t(B) * 4);
   L.node_order = o; o = al(o + size_t(B) * N * 4);
+  L.mol_launch = o; o = al(o + size_t(B) * 16);
+  L.atom_launch = o; o = al(o + size_t(B) * N * 16);
   L.total = o;
   return L;
 }
@@ -64,6 +66,8 @@ int make_plan(const void* plan_dev, int B, int N, int Mn, int Mp, Plan* p) {
   p->pair_rows = reinterpret_cast<const int2*>(base + L.pair_rows);
   p->mol_order = reinterpret_cast<const int*>(base + L.mol_order);
   p->node_order = reinterpret_cast<const int*>(base + L.node_order);
+  p->mol_launch = reinterpret_cast<const int4*>(base + L.mol_launch);
+  p->atom_launch = reinterpret_cast<const int4*>(base + L.atom_launch);
   return DS_OK;
 }
 
@@ -161,9 +165,17 @@ int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_d
     for (int b = 0; b < B; ++b) ord[b] = idx[b];
     // the same order atom by atom, for the kernels whose warps map to atoms
     int* nord = reinterpret_cast<int*>(host.data() + L.node_order);
+    int4* ml = reinterpret_cast<int4*>(host.data() + L.mol_launch);
+    int4* al4 = reinterpret_cast<int4*>(host.data() + L.atom_launch);
     int q = 0;
-    for (int b = 0; b < B; ++b)
-      for (int i = 0; i < na[idx[b]]; ++i) nord[q++] = noff[idx[b]] + i;
+    for (int b = 0; b < B; ++b) {
+      const int m = idx[b];
+      ml[b] = make_int4(m, na[m], noff[m], poff[m]);
+      for (int i = 0; i < na[m]; ++i) {
+        al4[q] = make_int4(noff[m] + i, m, (na[m] << 8) | i, poff[m]);
+        nord[q++] = noff[m] + i;
+      }
+    }
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   DS_CUDA_CHECK(cudaMemcpyAsync(plan_dev, host.data(), L.total, cudaMemcpyHostToDevice, s));

@@ -231,6 +231,9 @@ struct Plan {
   const int2* pair_rows;       // [Mp] atom rows (i, j) of each unordered pair
   const int* mol_order;        // [B] molecules by descending atom count (launch order of the per-molecule kernels)
   const int* node_order;       // [Mn] atom rows in that molecule order (launch order of the warp-per-atom kernels)
+  // the same two orders with everything a CTA / warp needs to start in ONE 16-byte load (instead of a chain of three):
+  const int4* mol_launch;      // [B]  (molecule, n_atoms, noff, poff) of the k-th molecule in launch order
+  const int4* atom_launch;     // [Mn] (atom row, molecule, n_atoms << 8 | index in molecule, poff) of the k-th atom in launch order
 };
 __device__ __forceinline__ int pair_index(int n, int i, int j) {   // i < j < n, row-major upper triangle
   return i * n - (i * (i + 1)) / 2 + (j - i - 1);

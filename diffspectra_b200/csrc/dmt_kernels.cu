@@ -325,8 +325,9 @@ __global__ void __launch_bounds__(256, 4) k_pos_rbf(Plan plan, int do_update, co
   __shared__ float sw[MAX_ATOMS * (MAX_ATOMS - 1)];
   __shared__ float sp[MAX_ATOMS][3];
   __shared__ float red[3][2];
-  const int mol = plan.mol_order[blockIdx.x], t = threadIdx.x;
-  const int n = plan.n_atoms[mol], base = plan.noff[mol], pbase = plan.poff[mol];
+  const int4 ml = __ldg(plan.mol_launch + blockIdx.x);
+  const int mol = ml.x, t = threadIdx.x;
+  const int n = ml.y, base = ml.z, pbase = ml.w;
   const int np = n * (n - 1) / 2;
   // issued before the position phase so that their latency overlaps it
   const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_RBF;
@@ -575,11 +576,12 @@ __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int
   __shared__ int srow[G][MAXN];
   __shared__ float sinv[G][N_HEADS];             // 1 / softmax denominator, applied once to the accumulated messages
   // CTAs are issued largest molecule first (plan.mol_order), so the kernel's tail is made of its cheapest CTAs
-  const int mol = plan.mol_order[blockIdx.x / ngrp], j0 = (blockIdx.x % ngrp) * G;
-  const int n = plan.n_atoms[mol];
+  const int4 ml = __ldg(plan.mol_launch + blockIdx.x / ngrp);      // (molecule, n, noff, poff): one load, not a chain of three
+  const int j0 = (blockIdx.x % ngrp) * G;
+  const int n = ml.y;
   if (j0 >= n) return;
   const int t = threadIdx.x;
-  const int base = plan.noff[mol], pbase = plan.poff[mol];
+  const int base = ml.z, pbase = ml.w;
   const int gsz = min(G, n - j0);
   for (int idx = t; idx < gsz * 64; idx += 32 * G) {     // q rows of the targets (252 values, padded to 256)
     const int jl = idx >> 6, c4 = idx & 63;
@@ -913,10 +915,9 @@ __global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* _
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mi = blockIdx.x * 8 + wi;
   if (mi >= plan.Mn) return;
-  const int m = plan.node_order[mi];         // atoms of the largest molecules first: the grid ends on its shortest warps
-  const uint32_t info = plan.node_info[m];
-  const int mol = info >> 6, r = info & 63;
-  const int n = plan.n_atoms[mol], pbase = plan.poff[mol];
+  // atoms of the largest molecules first (the grid ends on its shortest warps); (row, molecule, n << 8 | r, poff) in one load
+  const int4 al = __ldg(plan.atom_launch + mi);
+  const int m = al.x, mol = al.y, r = al.z & 255, n = al.z >> 8, pbase = al.w;
   const float* ar = ada + static_cast<size_t>(mol) * ADA_LD + l * ADA_BLK + ADA_COORD;
   float2 a2[4], sh2[4], sc2[4];      // channel pairs: the fp32 arithmetic below is packed (FADD2 / FFMA2)
   {
@@ -933,11 +934,17 @@ __global__ void __launch_bounds__(256) k_coord_ln_async(Plan plan, const bf16* _
   }
   const size_t d0 = static_cast<size_t>(2 * pbase) + static_cast<size_t>(r) * (n - 1);
   const int4* di = plan.dir_info + d0;       // x = pair row, z = atom row of the target (plan table, no index arithmetic)
+  // the warp's n - 1 table entries arrive with one coalesced load (two for N > 33) and are handed out by shuffles: no
+  // dependent index load stands between an iteration and the copies it starts
+  int2 dia = make_int2(0, 0), dib = make_int2(0, 0);
+  if (lane < n - 1) { const int4 t = __ldg(di + lane); dia = make_int2(t.x, t.z); }
+  if (lane + 32 < n - 1) { const int4 t = __ldg(di + lane + 32); dib = make_int2(t.x, t.z); }
   auto issue = [&](int cc) {                 // start the copies of target number cc (if any) and close its group
-    if (cc < n - 1) {
-      const int4 t = __ldg(di + cc);
-      cp_async16(&ring[wi][cc % kCoordDepth][0][lane], ab + static_cast<size_t>(t.z) * 512 + 256 + 8 * lane);
-      cp_async16(&ring[wi][cc % kCoordDepth][1][lane], gp + static_cast<size_t>(t.x) * 256 + 8 * lane);
+    if (cc < n - 1) {                        // warp-uniform
+      const int2 sel = cc < 32 ? dia : dib;
+      const int tx = __shfl_sync(0xffffffffu, sel.x, cc & 31), tz = __shfl_sync(0xffffffffu, sel.y, cc & 31);
+      cp_async16(&ring[wi][cc % kCoordDepth][0][lane], ab + static_cast<size_t>(tz) * 512 + 256 + 8 * lane);
+      cp_async16(&ring[wi][cc % kCoordDepth][1][lane], gp + static_cast<size_t>(tx) * 256 + 8 * lane);
     }
     cp_async_commit();
   };
