@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(256, 4) k_pos_rbf(Plan plan, int do_update, co
   __shared__ float sw[MAX_ATOMS * (MAX_ATOMS - 1)];
   __shared__ float sp[MAX_ATOMS][3];
   __shared__ float red[3][2];
+  __shared__ uint16_t sij[MAX_ATOMS * (MAX_ATOMS - 1) / 2];      // (i << 6 | j) of the molecule's pairs
   const int4 ml = __ldg(plan.mol_launch + blockIdx.x);
   const int mol = ml.x, t = threadIdx.x;
   const int n = ml.y, base = ml.z, pbase = ml.w;
@@ -347,6 +348,8 @@ __global__ void __launch_bounds__(256, 4) k_pos_rbf(Plan plan, int do_update, co
     for (int idx = t; idx < 2 * np; idx += 256) sw[idx] = wsrc[idx];
   }
   if (t < n * 3) (&sp[0][0])[t] = pos[static_cast<size_t>(base) * 3 + t];
+  // the pair table too (coalesced, same round trip): no dependent global load is left inside the RBF loop
+  for (int idx = t; idx < np; idx += 256) sij[idx] = static_cast<uint16_t>(__ldg(plan.pair_info + pbase + idx) & 0xfffu);
   __syncthreads();
   if (do_update) {
     float nx = 0.f, ny = 0.f, nz = 0.f;
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(256, 4) k_pos_rbf(Plan plan, int do_update, co
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       qq[u] = q0 + u * 32 + (t >> 3);
-      info[u] = __ldg(plan.pair_info + pbase + min(qq[u], np - 1));
+      info[u] = sij[min(qq[u], np - 1)];
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -598,6 +601,14 @@ __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int
     const int hh = idx & 15, r = idx >> 4;
     const int jl = static_cast<int>((static_cast<unsigned>(r) * rcp_n) >> 16), i = r - jl * n;
     const int row = srow[jl][i];
+    if (kFast && idx + 32 * G < gsz * n * N_HEADS) {
+      // the e0 row of this thread's NEXT item goes to L1 while the current one is computed: its 16 lanes cover the 512
+      // bytes with one 32-byte sector each (the rows come from L2 / HBM, everything else of an item is L1-resident)
+      const int r2 = (idx + 32 * G) >> 4;
+      const int jl2 = static_cast<int>((static_cast<unsigned>(r2) * rcp_n) >> 16);
+      const int row2 = srow[jl2][r2 - jl2 * n];
+      if (row2 >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(e01 + static_cast<size_t>(row2) * E01_LD + hh * (32 / sizeof(AT))));
+    }
     if (row < 0) continue;
     if (hh < N_SUB) {
       // head-interleaved channel order (common.cuh: head_perm): pair d of head hh sits at d * 28 + hh * 2, so the 14 lanes
