@@ -114,12 +114,14 @@ size_t ds_plan_bytes(int B, int N) {
   return plan_layout(B, N).total;
 }
 
-int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_dev, int* Mn_out, int* Mp_out, void* stream) {
-  DS_CHECK(h && n_atoms_host && plan_dev && Mn_out && Mp_out, DS_ERR_INVALID, "ds_plan_build: null argument");
+// Host side of the plan: every table of the blob (layout above) from the atom counts.  No CUDA call in here, so the
+// CPU tests can check it (ds_plan_build_host) against an independent restatement.
+static int fill_plan_host(const int* n_atoms_host, int B, int N, std::vector<uint8_t>& host, int* Mn_out, int* Mp_out) {
+  DS_CHECK(n_atoms_host && Mn_out && Mp_out, DS_ERR_INVALID, "ds_plan_build: null argument");
   DS_CHECK(B > 0 && B < (1 << 19), DS_ERR_INVALID, "ds_plan_build: B=%d out of range", B);
   DS_CHECK(N > 0 && N <= MAX_ATOMS, DS_ERR_INVALID, "ds_plan_build: N=%d out of range (1..%d)", N, MAX_ATOMS);
   const PlanLayout L = plan_layout(B, N);
-  std::vector<uint8_t> host(L.total, 0);
+  host.assign(L.total, 0);
   int* na = reinterpret_cast<int*>(host.data() + L.n_atoms);
   int* noff = reinterpret_cast<int*>(host.data() + L.noff);
   int* poff = reinterpret_cast<int*>(host.data() + L.poff);
@@ -177,11 +179,38 @@ int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_d
       }
     }
   }
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  DS_CUDA_CHECK(cudaMemcpyAsync(plan_dev, host.data(), L.total, cudaMemcpyHostToDevice, s));
-  DS_CUDA_CHECK(cudaStreamSynchronize(s));   // host staging buffer dies at return
   *Mn_out = mn;
   *Mp_out = mp;
+  return DS_OK;
+}
+
+
+int ds_plan_build(ds_ctx* h, const int* n_atoms_host, int B, int N, void* plan_dev, int* Mn_out, int* Mp_out, void* stream) {
+  DS_CHECK(h && plan_dev, DS_ERR_INVALID, "ds_plan_build: null argument");
+  std::vector<uint8_t> host;
+  DS_TRY(fill_plan_host(n_atoms_host, B, N, host, Mn_out, Mp_out));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DS_CUDA_CHECK(cudaMemcpyAsync(plan_dev, host.data(), host.size(), cudaMemcpyHostToDevice, s));
+  DS_CUDA_CHECK(cudaStreamSynchronize(s));   // host staging buffer dies at return
+  return DS_OK;
+}
+
+int ds_plan_build_host(const int* n_atoms_host, int B, int N, void* plan_host, size_t plan_bytes, int* Mn_out, int* Mp_out) {
+  DS_CHECK(plan_host != nullptr, DS_ERR_INVALID, "ds_plan_build_host: null argument");
+  std::vector<uint8_t> host;
+  DS_TRY(fill_plan_host(n_atoms_host, B, N, host, Mn_out, Mp_out));
+  DS_CHECK(plan_bytes >= host.size(), DS_ERR_INVALID, "ds_plan_build_host: buffer of %zu bytes, need %zu", plan_bytes, host.size());
+  memcpy(plan_host, host.data(), host.size());
+  return DS_OK;
+}
+
+int ds_plan_layout(int B, int N, size_t* offsets, int n_offsets) {
+  // byte offsets of the tables inside the plan blob, in declaration order (tests / debugging)
+  DS_CHECK(offsets != nullptr && n_offsets >= 13 && B > 0 && N > 0, DS_ERR_INVALID, "ds_plan_layout: need room for 13 offsets");
+  const PlanLayout L = plan_layout(B, N);
+  const size_t o[13] = {L.n_atoms, L.noff, L.poff, L.node_info, L.pair_info, L.dir_info, L.dir_mol, L.pair_rows, L.mol_order,
+                        L.node_order, L.mol_launch, L.atom_launch, L.total};
+  for (int i = 0; i < 13; ++i) offsets[i] = o[i];
   return DS_OK;
 }
 

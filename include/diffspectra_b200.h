@@ -77,6 +77,11 @@ int ds_pack_weights(ds_ctx* ctx, const char* const* names, const void* const* pt
 size_t ds_plan_bytes(int B, int N);
 int ds_plan_build(ds_ctx* ctx, const int* n_atoms_host, int B, int N, void* plan, int* Mn_out, int* Mp_out,
                   void* stream);
+/* The same blob into HOST memory (no CUDA call; what ds_plan_build copies to the device), and the byte offsets of its 12
+ * tables + the total size, in order: n_atoms, noff, poff, node_info, pair_info, dir_info, dir_mol, pair_rows, mol_order,
+ * node_order, mol_launch, atom_launch, total.  Used by the CPU tests of the host logic. */
+int ds_plan_build_host(const int* n_atoms_host, int B, int N, void* plan_host, size_t plan_bytes, int* Mn_out, int* Mp_out);
+int ds_plan_layout(int B, int N, size_t* offsets, int n_offsets);
 
 size_t ds_workspace_bytes(ds_ctx* ctx, int B, int Mn, int Mp);
 size_t ds_specformer_workspace_bytes(ds_ctx* ctx, int B);
