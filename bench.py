@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """Benchmark of the DiffSpectra sampling hot path (BASELINE.json: molecules/s, QM9S allspectra, 1000 steps).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--diffusion-steps S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload configs1|eval10k|wo_eq|n64]
 
-One bench "step" = one sampling ROUND of the reference eval driver (sampling.py:390-465): a batch of B=1024
-synthetic QM9S-shaped molecules (atom counts from the QM9S histogram, allspectra SpecFormer conditioning) taken
-through SpecFormer + S=1000 reverse-diffusion steps + post_process.  value = molecules/s over K rounds (whole job,
-all ranks); `e2e` = the same through the public API with HOST spectra in pinned memory (H2D inside the timed region)
-and the generated molecules copied back to the host.  N > 1: one process per GPU (torchrun), independent shards
-(weak scaling), one NCCL all-gather of the packed molecule records per round.
+One bench "step" = one sampling ROUND of the reference eval driver (sampling.py:390-465): SpecFormer + S=1000
+reverse-diffusion steps + molecule records.  Workloads (BASELINE.json `configs`):
+  configs1 (default)  configs[1]: DMT allspectra, batch 1024 per GPU, QM9S atom-count histogram; weak scaling
+  eval10k             configs[2]: 10 000 samples x 1000 steps, STRONG scaling: every rank samples ceil(10000/G) molecules
+                      in ONE round (1250 per GPU at 8), one all-gather of the records inside the timed region
+  wo_eq               configs[3]: the DMT_WO_EQ ablation, batch 1024 per GPU
+  n64                 configs[4]: stress shape, 64 atoms per molecule, batch 512 per GPU
+`value` = molecules/s with the spectra already resident in HBM (Engine calls: SpecFormer -> loop -> records -> gather);
+`e2e` = the same through the PUBLIC API — `get_cond_sampling_eval_fn(config, ...)(model)` (sampling.py:353-468) on an
+in-memory data set with HOST spectra: staging, H2D, plan build, weight fingerprint, SpecFormer, the loop, records, the
+all-gather, ONE D2H copy and the conversion to the reference's per-molecule tuples all inside the timed region.
 
 `--impl reference` times the reference's own algorithm on the host CPU cores (the oracle port of the PyTorch path:
 /root/reference is a Python repo that is not present on the GPU box) on a bounded sample of the same workload.
+The CUDA arm imports nothing from oracle/ except for the `cpu_baseline` leg.
 """
 import argparse
 import json
@@ -101,6 +107,45 @@ def host_threads():
     return torch.get_num_threads()
 
 
+def cpu_configs0(repeats=3):
+    """BASELINE.json configs[0] AS WRITTEN: reference path (oracle port), IR-only SpecFormer, B = 16
+    molecules (QM9S histogram, molecule 0 with 29 atoms), N_pad = 29, 50-step ancestral sampling, fp32, timed in full
+    (no extrapolation); `repeats` runs after one warm-up denoiser call.  Returns dict(min/median/max seconds, rates)."""
+    import torch
+    host_threads()
+    from diffspectra_b200.config import get_config
+    from diffspectra_b200.model import DMT_B200
+    from oracle import dense_oracle as O
+    from oracle import weights as W
+    B, N, steps, version = 16, 29, 50, 'ir'
+    torch.manual_seed(42)
+    sd = DMT_B200(get_config(version, device='cpu')).state_dict()
+    n = W.sample_n_atoms(B, seed=1234)
+    nm, em = W.make_masks(n, N)
+    ctx = W.synthetic_spectra(B, version, seed=1235)
+    table = O.schedule_table(steps)
+    g = torch.Generator().manual_seed(42)
+    z = O.node_noise_from_raw(torch.randn(B, N, 3, generator=g), torch.randn(B, N, 6, generator=g), nm)
+    ez = O.edge_noise_from_raw(torch.randn(B, 2, N, N, generator=g), em)
+    raw = [O.draw_step_noise(B, N, nm, em, generator=g) for _ in range(steps)]
+
+    def denoise(x, ex, nl, cx, cex):          # the reference re-runs SpecFormer inside every call (dmt.py:348-350)
+        return O.dmt_forward(sd, x, nm, em, ex, nl, cx, cex, O.context_embedding(sd, ctx, version))
+
+    secs = []
+    with torch.no_grad():
+        denoise(z, ez, torch.full((B,), -9.5), None, None)        # warm-up call
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.ancestral_sample(denoise, table, z, ez, nm, em, raw)
+            secs.append(time.perf_counter() - t0)
+    secs.sort()
+    return {'workload': 'BASELINE configs[0]: DMT + IR-only SpecFormer, B=16 (QM9S histogram), N_pad=29, 50-step ancestral '
+                        'sampling, fp32, timed in full', 'repeats': repeats, 'seconds_min': secs[0],
+            'seconds_median': secs[len(secs) // 2], 'seconds_max': secs[-1], 'molecules_per_s_best': B / secs[0],
+            'denoiser_steps_per_s_best': steps / secs[0], 'spread': (secs[-1] - secs[0]) / secs[0]}
+
+
 def cpu_reference_rate(sample_b=16, sample_steps=4, repeats=1, model='DMT', n_pad=29, all_max=False):
     """Oracle port of the reference PyTorch path (dense restatement, oracle/dense_oracle.py) on the host cores,
     allspectra, on `sample_b` molecules x `sample_steps` denoiser steps (+ one SpecFormer pass per step, as the
@@ -144,33 +189,74 @@ def cpu_reference_rate(sample_b=16, sample_steps=4, repeats=1, model='DMT', n_pa
     return rate, best, desc
 
 
+WORKLOADS = {
+    # name: (model, per-GPU batch (None: strong), n_pad, all_max, total molecules (strong) or None, BASELINE tag)
+    'configs1': dict(model='DMT', batch=1024, n_pad=29, all_max=False, total=None, tag='BASELINE.json configs[1]'),
+    'eval10k': dict(model='DMT', batch=None, n_pad=29, all_max=False, total=10000, tag='BASELINE.json configs[2]'),
+    'wo_eq': dict(model='DMT_WO_EQ', batch=1024, n_pad=29, all_max=False, total=None, tag='BASELINE.json configs[3]'),
+    'n64': dict(model='DMT', batch=512, n_pad=64, all_max=True, total=None, tag='BASELINE.json configs[4] stress shape'),
+}
+
+
+def resolve_workload(args, world):
+    w = dict(WORKLOADS[args.workload])
+    if args.model is not None:
+        w['model'] = args.model
+    if args.n_pad is not None:
+        w['n_pad'] = args.n_pad
+        w['all_max'] = w['all_max'] or args.n_pad > 29
+    if args.all_max:
+        w['all_max'] = True
+    if args.batch is not None:
+        w['batch'] = args.batch
+        w['total'] = None
+    if w['total'] is not None:                     # strong scaling: one round of ceil(total / G) molecules per rank
+        w['batch'] = -(-w['total'] // world)
+    w['strong'] = w['total'] is not None
+    if args.model is not None or args.n_pad is not None or args.batch is not None or args.all_max:
+        w['tag'] = 'custom (derived from %s)' % w['tag']
+    return w
+
+
+def workload_name(args, w=None):
+    w = w or resolve_workload(args, max(1, args.gpus))
+    if w['strong']:
+        return '%s allspectra sampling, %d steps, %d molecules in total sharded over the GPUs (%d per GPU, one round), N<=%d (%s)' % (
+            w['model'], args.diffusion_steps, w['total'], w['batch'], w['n_pad'], w['tag'])
+    return '%s allspectra sampling, %d steps, batch %d per GPU, N<=%d (%s)' % (w['model'], args.diffusion_steps, w['batch'],
+                                                                              w['n_pad'], w['tag'])
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    w = resolve_workload(args, max(1, args.gpus))
     cores = host_threads()
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_rate(8, 1, model=args.model, n_pad=args.n_pad, all_max=args.all_max)
+        cpu_reference_rate(8, 1, model=w['model'], n_pad=w['n_pad'], all_max=w['all_max'])
     rates, secs = [], 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r, s, desc = cpu_reference_rate(16, 2, model=args.model, n_pad=args.n_pad, all_max=args.all_max)
+        r, sec, desc = cpu_reference_rate(16, 2, model=w['model'], n_pad=w['n_pad'], all_max=w['all_max'])
         rates.append(r)
-        secs += s
+        secs += sec
         if time.perf_counter() - t0 > 150:
             break
     value = len(rates) * 16 / sum(16 / r for r in rates)
+    c0 = cpu_configs0(repeats=args.cpu_repeats) if (w['model'] == 'DMT' and w['n_pad'] == 29 and args.cpu_repeats > 0) else None
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(rates),
-        'warmup': min(args.warmup, 1), 'ms_per_step': 1000.0 * args.batch / value, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'warmup': min(args.warmup, 1), 'ms_per_step': 1000.0 * w['batch'] / value, 'higher_is_better': True,
+        'scaling': 'strong' if w['strong'] else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         # same workload keys as the CUDA arm's line; the CPU arm times a bounded sample of it (cpu_baseline.sample)
-        'config': {'workload': workload_name(args), 'model': args.model + ' (oracle port of the reference PyTorch path)',
-                   'batch_per_gpu': args.batch, 'diffusion_steps': args.diffusion_steps, 'n_pad': args.n_pad,
-                   'n_atoms': 'all %d' % args.n_pad if args.all_max else 'QM9S histogram', 'noise': 'torch generator',
+        'config': {'workload': workload_name(args, w), 'model': w['model'] + ' (oracle port of the reference PyTorch path)',
+                   'batch_per_gpu': w['batch'], 'diffusion_steps': args.diffusion_steps, 'n_pad': w['n_pad'],
+                   'n_atoms': 'all %d' % w['n_pad'] if w['all_max'] else 'QM9S histogram', 'noise': 'torch generator',
                    'sample': desc, 'parallelism': 'host threads: %d' % cores},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc,
+                         'value_min': min(rates), 'value_max': max(rates), 'configs0': c0},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -183,11 +269,13 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from diffspectra_b200 import build as B
+    from diffspectra_b200 import evaluate as E
+    from diffspectra_b200 import sampling as SMP
+    from diffspectra_b200 import synthetic as SY
     from diffspectra_b200.config import get_config
-    from diffspectra_b200.distributed import gather_records, pack_records
+    from diffspectra_b200.distributed import gather_records, record_bytes
     from diffspectra_b200.model import DMT_B200, DMT_WO_EQ_B200
     from diffspectra_b200.noise_schedule import NoiseScheduleVP, ancestral_coefficients
-    from oracle import weights as W          # synthetic inputs only (atom-count histogram, spectra)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -211,94 +299,126 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
 
-    Bsz, S, N_PAD = args.batch, args.diffusion_steps, args.n_pad
+    w = resolve_workload(args, world)
+    Bsz, S, N_PAD = w['batch'], args.diffusion_steps, w['n_pad']
     torch.manual_seed(42)                                   # random-init weights of the reference architecture
-    cls = DMT_B200 if args.model == 'DMT' else DMT_WO_EQ_B200
-    model = cls(get_config(VERSION, device=str(dev), precision=args.precision)).eval().to(dev)
+    cls = DMT_B200 if w['model'] == 'DMT' else DMT_WO_EQ_B200
+    config = get_config(VERSION, device=str(dev), precision=args.precision)
+    config.sampling.steps = S
+    config.data.max_node = N_PAD
+    model = cls(config).eval().to(dev)
     eng = model.engine(dev)
-    n_atoms = W.sample_n_atoms(Bsz, seed=1234 + rank, max_n=min(N_PAD, 29)).numpy().astype(np.int32)
-    if args.all_max:
-        n_atoms[:] = N_PAD
+    # the data set of the whole job (all ranks build the same one): rank r's shard = items [r*Bsz, (r+1)*Bsz) of the
+    # driver's permutation; the device-resident leg uses the same atom counts / spectra without the permutation
+    n_items = Bsz * world
+    n_all = SY.sample_n_atoms(n_items, seed=1234, max_n=min(N_PAD, 29))
+    if w['all_max']:
+        n_all[:] = N_PAD
+    if w['strong'] and w['total'] is not None:
+        n_items = w['total']
+        n_all = n_all[:n_items]
+    ds = SY.SyntheticQM9S(n_items, VERSION, seed=1235, n_atoms=n_all, pin=True)
+    lo = min(rank * Bsz, n_items)
+    hi = min(lo + Bsz, n_items)
+    n_atoms = n_all[lo:hi].numpy().astype(np.int32)
+    B_loc = int(hi - lo)
     plan = eng.plan(n_atoms, N_PAD)
-    spectra_host = [t.pin_memory() for t in W.synthetic_spectra(Bsz, VERSION, seed=1235 + rank)]
-    spectra_dev = [t.to(dev) for t in spectra_host]
+    spectra_dev = [getattr(ds._data, k)[lo:hi].to(dev) for k in ds.keys]
     ns = NoiseScheduleVP('cosine', continuous_beta_0=0.1, continuous_beta_1=20.)
     coef = ancestral_coefficients(ns, torch.linspace(ns.T, 1e-3, S, device=dev))
-    out = (torch.empty(Bsz, N_PAD, 9, device=dev), torch.empty(Bsz, N_PAD, N_PAD, 2, device=dev))
-    rec_host = None
+    out = (torch.empty(B_loc, N_PAD, 9, device=dev), torch.empty(B_loc, N_PAD, N_PAD, 2, device=dev))
+    pad = None
+    if B_loc < Bsz:                                          # short last shard of the strong-scaling split
+        pad = torch.zeros(Bsz - B_loc, record_bytes(N_PAD), dtype=torch.uint8, device=dev)
 
-    def one_round(r, e2e):
-        nonlocal rec_host
-        sp = [t.to(dev, non_blocking=True) for t in spectra_host] if e2e else spectra_dev
-        ctx_emb = eng.context_embedding(sp)
+    def resident_round(r):
+        """Inputs already in HBM: SpecFormer -> 1000-step loop -> record kernel -> (all-gather)."""
+        ctx_emb = eng.context_embedding(spectra_dev)
         eng.sample_loop(plan, ctx_emb, coef, None, None, None, seed=42, gid_base=(r * world + rank) * Bsz,
                         temperature=1.0, use_graph=True, out=out)
-        pos, atom, fc, bond = eng.post_process(plan, out[0], out[1])
-        rec = pack_records(pos, atom, fc, bond, torch.as_tensor(n_atoms, device=dev))
+        rec = eng.molecule_records(plan, out[0], out[1], N_PAD)
+        if pad is not None:
+            rec = torch.cat([rec, pad])
         if world > 1:
             rec = gather_records(rec)                        # the single collective of the path (SURVEY.md §8(e))
-        if e2e:
-            if rec_host is None or rec_host.shape != rec.shape:
-                rec_host = torch.empty(rec.shape, dtype=rec.dtype, pin_memory=True)
-            rec_host.copy_(rec, non_blocking=True)
         return rec
 
-    def timed(k, e2e, base):
+    # the public API: the reference's eval-driver factory (sampling.py:353) -> sampling_fn(model)
+    if world > 1:
+        api_fn = E.get_cond_sampling_eval_fn(config, ns, Bsz, n_items, None, ds, noise='philox', seed=42)
+    else:
+        api_fn = SMP.get_cond_sampling_eval_fn(config, ns, Bsz, n_items, None, ds, noise='philox', seed=42)
+    n_out = [0]
+
+    def api_round(r):
+        mols, tpos, _ = api_fn(model)
+        n_out[0] = len(mols)
+        return mols
+
+    def timed(k, fn, base):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launch_count()
+        t0 = time.perf_counter()
         e0.record()
         for i in range(k):
-            one_round(base + i, e2e)
+            fn(base + i)
         e1.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        wall = (time.perf_counter() - t0) * 1000.0
+        ms = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall], device=dev)
         if world > 1:
             dist.barrier()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), eng.launch_count() - l0
+        return ms[0].item(), ms[1].item(), eng.launch_count() - l0
 
     with torch.no_grad():
         for i in range(args.warmup):
-            one_round(i, False)
+            resident_round(i)
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
-        ms, launches = timed(args.steps, False, args.warmup)
+        ms, _, launches = timed(args.steps, resident_round, args.warmup)
         clk = clocks.stop() if rank == 0 else None
-        one_round(0, True)
-        ms_e2e, _ = timed(args.steps, True, args.warmup + args.steps)
-        kern = step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args) if rank == 0 else None
+        api_round(0)                                        # warm the API path (pinned buffers, caches)
+        ms_e2e_dev, ms_e2e_wall, _ = timed(args.steps, api_round, 1)
+        ms_e2e = max(ms_e2e_dev, ms_e2e_wall)               # the host tail (records -> tuples) is part of the call
+        kern = step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args, w) if rank == 0 else None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peaks = load_peaks()
-    mols = Bsz * world * args.steps
+    mols = n_items * args.steps
     value = mols / (ms / 1000.0)
     e2e_value = mols / (ms_e2e / 1000.0)
-    flops_round = float(sum(alg_flops(int(n), args.model) for n in n_atoms)) * S            # rank 0's shard, denoiser only
+    assert n_out[0] == n_items, (n_out[0], n_items)
+    flops_round = float(sum(alg_flops(int(n), w['model']) for n in n_atoms)) * S            # rank 0's shard, denoiser only
     achieved = flops_round * args.steps / (ms / 1000.0) / 1e12                  # TFLOP/s per GPU
-    h2d = sum(t.numel() * 4 for t in spectra_host) + n_atoms.nbytes
-    d2h = int(rec_host.numel() * rec_host.element_size()) if rec_host is not None else 0
-    cpu_rate, cpu_s, cpu_desc = (cpu_reference_rate(16, 2, model=args.model, n_pad=N_PAD, all_max=args.all_max)
-                                 if args.cpu_baseline else (None, 0, 'skipped (--no-cpu-baseline)'))
+    h2d = sum(getattr(ds._data, k)[lo:hi].numel() * 4 for k in ds.keys) + plan.buf.numel()    # spectra + plan tables, per rank
+    d2h = Bsz * world * record_bytes(N_PAD) + n_atoms.nbytes
+    if args.cpu_baseline:
+        cpu_rate, cpu_s, cpu_desc = cpu_reference_rate(16, 2, model=w['model'], n_pad=N_PAD, all_max=w['all_max'])
+        c0 = cpu_configs0(repeats=args.cpu_repeats) if (w['model'] == 'DMT' and N_PAD == 29 and args.cpu_repeats > 0) else None
+    else:
+        cpu_rate, cpu_desc, c0 = None, 'skipped (--no-cpu-baseline)', None
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if w['strong'] else 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args), 'model': args.model + '_B200',
-                   'batch_per_gpu': Bsz, 'diffusion_steps': S, 'n_pad': N_PAD,
-                   'n_atoms': 'all %d' % N_PAD if args.all_max else 'QM9S histogram, mean %.2f' % n_atoms.mean(),
+        'config': {'workload': workload_name(args, w), 'model': w['model'] + '_B200',
+                   'batch_per_gpu': Bsz, 'molecules_per_step': n_items, 'diffusion_steps': S, 'n_pad': N_PAD,
+                   'n_atoms': 'all %d' % N_PAD if w['all_max'] else 'QM9S histogram, mean %.2f' % n_atoms.mean(),
                    'noise': 'device Philox', 'l2': 'inputs_exceed_l2 (per-step working set >> 126 MB)',
                    'parallelism': 'dp%d independent shards + 1 all-gather/round' % world},
         'denoiser_steps_per_s': args.steps * S / (ms / 1000.0),
         'molecule_steps_per_s': value * S,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': d2h,
-                'ms_per_step': ms_e2e / args.steps},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'ms_per_step': ms_e2e / args.steps, 'ms_per_step_device': ms_e2e_dev / args.steps,
+                'api': 'get_cond_sampling_eval_fn(config, ...)(model) on an in-memory data set with pinned host spectra'},
         'gpu_launches': int(launches),
         'clocks': clk,
         'roofline': dict(kern['dominant'], step={
@@ -306,19 +426,11 @@ def run_ours(args):
             'what': 'whole denoiser step: algorithmic FLOPs per molecule-step (SURVEY.md 8(d); bench.alg_flops) / CUDA-event time '
                     'of the timed rounds; peak = sustained bf16, ' + peaks['which']}, kernels=kern['kernels'],
             in_stream_step_us=kern['step_us']),
-        'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port', 'sample': cpu_desc},
+        'cpu_baseline': {'value': cpu_rate, 'unit': UNIT, 'cores': host_threads(), 'kind': 'port', 'sample': cpu_desc, 'configs0': c0},
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def workload_name(args):
-    tag = {29: 'BASELINE.json configs[1]', 64: 'BASELINE.json configs[4] stress shape'}.get(args.n_pad, 'custom shape')
-    if args.model != 'DMT':
-        tag = 'BASELINE.json configs[3]' if args.n_pad == 29 else tag
-    return '%s allspectra sampling, %d steps, batch %d per GPU, N<=%d (%s)' % (args.model, args.diffusion_steps, args.batch,
-                                                                              args.n_pad, tag)
 
 
 def _demangle(name):
@@ -331,13 +443,31 @@ def _demangle(name):
     return base
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch (MB) from the committed `ncu --set full` capture of this
-# command at batch 1024 / QM9S histogram (profiles/r1_final3_ncu.md); reported as roofline.traffic for the same workload only
-NCU_DRAM_MB = {'k_attention_grp': 212.3, 'k_coord_ln_async': 227.7, 'gemm_tc_kernel<256,COORD,0>': 171.5, 'edge_ffn_kernel': 74.2,
-               'gemm_tc_kernel<64,LNMOD,1>': 43.3, 'k_pos_rbf': 2.3}
+def csrc_sha():
+    """sha256 over the CUDA sources + the header: identifies the build a profile was taken from (the GPU box has no .git)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'diffspectra_b200', 'csrc')
+    for f in sorted(os.listdir(d)) + ['../../include/diffspectra_b200.h']:
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), 'rb').read())
+    return h.hexdigest()[:16]
 
 
-def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
+def ncu_dram_table():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/ncu_dram.json, written by scratch/ncu_dram.py from the .ncu-rep of `bench.py --workload configs1`).  Only
+    returned when the capture was taken from THIS build (same csrc_sha): a stale table is never reported as traffic."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_dram.json')
+    if not os.path.isfile(p):
+        return {}, 'no capture (profiles/ncu_dram.json missing)'
+    d = json.load(open(p))
+    if d.get('csrc_sha') != csrc_sha():
+        return {}, 'capture %s is from another build (csrc_sha %s != %s)' % (d.get('source'), d.get('csrc_sha'), csrc_sha())
+    return d.get('kernels', {}), '%s (csrc_sha %s)' % (d.get('source'), d.get('csrc_sha'))
+
+
+def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args, w):
     """Every kernel of a denoiser step timed IN STREAM with CUDA events (ds_profile_begin/end around a non-graph
     ds_sample_loop of 3 steps, warm caches, same inputs as the timed region).  For each kernel: average launch time,
     ALGORITHMIC bytes / FLOPs per launch and the fraction of the HBM / tensor peak they amount to.
@@ -357,7 +487,7 @@ def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
     L.check(lib.ds_profile_end(buf, ctypes.c_size_t(len(buf))), 'ds_profile_end')
     Mn, Mp = plan.Mn, plan.Mp
     Md = 2 * Mp
-    wo = args.model != 'DMT'
+    wo = w['model'] != 'DMT'
     Me = Md if wo else Mp                       # rows of the edge tensors
     bytes_of = {      # ALGORITHMIC bytes per launch of the graph-side kernels (what must cross HBM once)
         'k_attention_grp': Mp * 1024 + Mp + Mn * (1536 + 256 * 6),          # e0|e1 once per pair, flags, q|k|v, hn fp32+bf16
@@ -405,6 +535,10 @@ def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
     rows.sort(key=lambda r: -r['us_per_step'])
     top = rows[0]
     tensor_bound = top.get('frac_tensor', 0) > top.get('frac_hbm', 0)
+    dram, dram_src = ncu_dram_table()
+    for r in rows:
+        if args.workload == 'configs1' and r['kernel'] in dram:
+            r['ncu_dram_bytes'] = dram[r['kernel']]
     dominant = {
         'kernel': top['kernel'] + (' ' + top['shape'] if 'shape' in top else ''),
         'bound': 'tensor' if tensor_bound else 'hbm',
@@ -412,12 +546,13 @@ def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args):
         'peak': peaks['burst'] if tensor_bound else peaks['hbm'],
         'unit': 'TFLOP/s' if tensor_bound else 'GB/s',
         'frac': top.get('frac_tensor') if tensor_bound else top.get('frac_hbm'),
-        'traffic': (NCU_DRAM_MB.get(top['kernel']) * 1e6 if (args.model == 'DMT' and args.batch == 1024 and args.n_pad == 29 and not args.all_max
-                                                             and top['kernel'] in NCU_DRAM_MB) else None),
+        'traffic': (dram[top['kernel']] if (args.workload == 'configs1' and w['tag'] == WORKLOADS['configs1']['tag'] and top['kernel'] in dram)
+                    else None),
+        'traffic_source': dram_src,
         'us_per_launch': top['us_per_launch'], 'share_of_step': top['share_of_step'],
         'what': 'dominant kernel of a denoiser step by in-stream CUDA-event time; achieved = algorithmic bytes (or FLOPs) per '
                 'launch / average launch time; peak = ' + peaks['which'] + ' (burst figures); traffic = ncu dram bytes per launch '
-                '(profiles/r1_final3_ncu.md), bytes',
+                '(profiles/ncu_dram.json, only when taken from this build), bytes',
     }
     return {'dominant': dominant, 'kernels': rows[:14], 'step_us': total / steps}
 
@@ -428,16 +563,16 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=1024)
+    ap.add_argument('--workload', default='configs1', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=None, help='override the per-GPU batch of the workload')
     ap.add_argument('--diffusion-steps', type=int, default=1000)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--model', default='DMT', choices=['DMT', 'DMT_WO_EQ'])
-    ap.add_argument('--n-pad', type=int, default=29, help='padded atoms per molecule (64 = stress shape, implies --all-max)')
+    ap.add_argument('--model', default=None, choices=['DMT', 'DMT_WO_EQ'], help='override the model of the workload')
+    ap.add_argument('--n-pad', type=int, default=None, help='override the padded atoms per molecule (> 29 implies --all-max)')
     ap.add_argument('--all-max', '--all29', dest='all_max', action='store_true', help='worst case: every molecule has n_pad atoms')
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
+    ap.add_argument('--cpu-repeats', type=int, default=3, help='full runs of BASELINE configs[0] on the host cores (0 = skip)')
     args = ap.parse_args()
-    if args.n_pad > 29:
-        args.all_max = True            # BASELINE.json configs[4]: synthetic molecules with N atoms each
     if args.impl == 'reference':
         run_reference(args)
     else:

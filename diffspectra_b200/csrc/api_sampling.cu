@@ -421,4 +421,20 @@ int ds_post_process(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int M
   return launch_post_process(c, plan, lw.xs, lw.es, pos, atom_type, formal_charge, bond, s);
 }
 
+size_t ds_record_bytes(int N) { return N > 0 ? static_cast<size_t>(N) * 14 + static_cast<size_t>(N) * N + 1 : 0; }
+
+int ds_molecule_records(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp, const float* x_mean, const float* edge_mean,
+                        int rec_n, void* records, size_t records_bytes, void* stream) {
+  CtxFull* c = full(h);
+  DS_CHECK(c && x_mean && edge_mean && records, DS_ERR_INVALID, "ds_molecule_records: null argument");
+  DS_CHECK(rec_n >= N && rec_n <= 255, DS_ERR_INVALID, "ds_molecule_records: rec_n=%d must be in [N=%d, 255]", rec_n, N);
+  const size_t rb = ds_record_bytes(rec_n);
+  DS_CHECK(records_bytes >= rb * static_cast<size_t>(B), DS_ERR_WORKSPACE, "ds_molecule_records: %zu bytes given, %zu needed", records_bytes,
+           rb * static_cast<size_t>(B));
+  Plan plan;
+  DS_TRY(make_plan(plan_dev, B, N, Mn, Mp, &plan));
+  return launch_molecule_records(c, plan, x_mean, edge_mean, static_cast<uint8_t*>(records), rec_n, static_cast<int>(rb),
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -195,6 +195,9 @@ int launch_step_inc(DsContext* ctx, int* step, cudaStream_t s);
 int launch_post_process(DsContext* ctx, const Plan& plan, const float* xs, const float* es, float* pos, int* atom_type,
                         int* fc, float* bond, cudaStream_t s);
 
+int launch_molecule_records(DsContext* ctx, const Plan& plan, const float* x_mean, const float* edge_mean, uint8_t* rec,
+                            int rec_n, int rec_bytes, cudaStream_t s);
+
 struct SpecWs {
   float* z; void* zb; float* qkv; float* scores; void* att; float* o; void* f; float* head; void* hb;
 };

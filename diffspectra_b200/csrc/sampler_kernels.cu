@@ -253,7 +253,64 @@ __global__ void k_post_pairs(Plan plan, const float* __restrict__ es, float* __r
   bond[idx] = v;
 }
 
+// Molecule records straight from the reference-shaped means (sampling.py:12-32 mol_process + :53-97 post_process in one
+// pass): record b = pos f32[R*3] | atom u8[R] | fc i8[R] | bond u8[R*R] | n u8, rec_bytes = 14 R + R^2 + 1 (1248 B at
+// R = 29), R = rec_n >= N (rounds whose padded size N is smaller than the data set's max_node still emit full-size
+// records).  This is the unit of the ONE all-gather of a sampling round and of the single D2H copy of the eval driver.
+// One CTA per molecule; bytes are written individually (the record stride is not a multiple of 4 for every R).
+__global__ void __launch_bounds__(256) k_molecule_records(Plan plan, const float* __restrict__ x, const float* __restrict__ ex,
+                                                          uint8_t* __restrict__ rec, int R, int rec_bytes) {
+  pdl_trigger();
+  pdl_wait();
+  const int mol = blockIdx.x, N = plan.N, n = plan.n_atoms[mol], t = threadIdx.x;
+  uint8_t* r = rec + static_cast<size_t>(mol) * rec_bytes;
+  const float* xm = x + static_cast<size_t>(mol) * N * 9;
+  for (int idx = t; idx < R * 3; idx += 256) {
+    const int a = idx / 3, c = idx - a * 3;
+    const uint32_t u = __float_as_uint(a < n ? xm[a * 9 + c] : 0.f);
+    r[idx * 4 + 0] = u & 0xff; r[idx * 4 + 1] = (u >> 8) & 0xff; r[idx * 4 + 2] = (u >> 16) & 0xff; r[idx * 4 + 3] = u >> 24;
+  }
+  uint8_t* ra = r + R * 12;
+  for (int a = t; a < R; a += 256) {
+    int ty = 0, q = 0;
+    if (a < n) {
+      const float* xr = xm + a * 9;
+      float best = (xr[3] * 4.0f + 1.0f) / 2.0f;           // same arithmetic as k_post_nodes
+      for (int c = 1; c < 5; ++c) {
+        const float v = (xr[3 + c] * 4.0f + 1.0f) / 2.0f;
+        if (v > best) { best = v; ty = c; }
+      }
+      q = static_cast<int>(rintf(xr[8] * 4.0f));
+    }
+    ra[a] = static_cast<uint8_t>(ty);
+    ra[R + a] = static_cast<uint8_t>(static_cast<int8_t>(q));
+  }
+  uint8_t* rb = r + R * 14;
+  const float* em = ex + static_cast<size_t>(mol) * N * N * 2;
+  for (int idx = t; idx < R * R; idx += 256) {
+    const int i = idx / R, j = idx - i * R;
+    uint8_t v = 0;
+    if (i < n && j < n && i != j) {
+      const int lo = i < j ? i : j, hi = i < j ? j : i;     // the packed state keeps (lo, hi): same element as k_post_pairs
+      const float* e = em + (static_cast<size_t>(lo) * N + hi) * 2;
+      const float exv = (e[0] + 1.0f) / 2.0f;
+      const float tv = (e[1] + 1.0f) / 2.0f * 3.0f;
+      const int order = tv >= 2.5f ? 3 : (tv >= 1.5f ? 2 : (tv >= 0.5f ? 1 : 0));
+      v = static_cast<uint8_t>(exv >= 0.5f ? order : 0);
+    }
+    rb[idx] = v;
+  }
+  if (t == 0) r[R * 14 + R * R] = static_cast<uint8_t>(n);
+}
+
 }  // namespace
+
+int launch_molecule_records(DsContext* ctx, const Plan& plan, const float* x_mean, const float* edge_mean, uint8_t* rec,
+                            int rec_n, int rec_bytes, cudaStream_t s) {
+  ds_launch(k_molecule_records, dim3(plan.B), dim3(256), 0, s, plan, x_mean, edge_mean, rec, rec_n, rec_bytes);
+  LAUNCH_CHECK(ctx);
+  return DS_OK;
+}
 
 int launch_pack_dense(DsContext* ctx, const Plan& plan, const float* x, const float* ex, float* xs, float* es, cudaStream_t s) {
   if (x) {

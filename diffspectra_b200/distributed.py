@@ -19,7 +19,9 @@ def record_bytes(N):
 
 
 def pack_records(pos, atom_type, fc, bond, n_atoms):
-    """[B, record_bytes(N)] uint8: pos f32[N*3] | atom u8[N] | fc i8[N] | bond u8[N*N] | n u8."""
+    """[B, record_bytes(N)] uint8: pos f32[N*3] | atom u8[N] | fc i8[N] | bond u8[N*N] | n u8.
+    Host / eager restatement of the record layout, kept for the CPU tests of the gather logic and as the checker of the
+    device kernel (ds_molecule_records, Engine.molecule_records), which is what the product path uses."""
     B, N = atom_type.shape
     return torch.cat([pos.contiguous().view(torch.uint8).reshape(B, N * 12),
                       atom_type.to(torch.uint8),

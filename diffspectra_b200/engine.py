@@ -196,3 +196,15 @@ class Engine:
                                         L.ptr(fc), L.ptr(bond), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream_ptr()),
                 'ds_post_process')
         return pos, atom, fc, bond
+
+    def molecule_records(self, plan, x_mean, edge_mean, rec_n=None):
+        """[B, ds_record_bytes(rec_n)] uint8 on the device: pos f32[R*3] | atom u8[R] | fc i8[R] | bond u8[R*R] | n u8, written
+        by one kernel from the means of the last step (post_process + mol_process, sampling.py:12-32,53-97)."""
+        B, N = plan.B, plan.N
+        rec_n = N if rec_n is None else max(int(rec_n), N)
+        x_mean, edge_mean = self._dev(x_mean), self._dev(edge_mean)
+        rb = int(L.lib().ds_record_bytes(rec_n))
+        rec = torch.empty(B, rb, dtype=torch.uint8, device=self.device)
+        L.check(L.lib().ds_molecule_records(self.h, *plan.args(), L.ptr(x_mean), L.ptr(edge_mean), rec_n, L.ptr(rec),
+                                            ctypes.c_size_t(rec.numel()), L.stream_ptr()), 'ds_molecule_records')
+        return rec

@@ -89,14 +89,24 @@ def get_cond_sampling_eval_fn(config, noise_scheduler, batch_size, n_samples, in
     N = int(getattr(config.data, 'max_node', 0) or 29)
 
     def sampling_fn(model):
-        local_mols, _, _ = local_fn(model)
-        if world == 1:
-            mols = local_mols
-        else:
-            total = min(n_samples, len(test_ds))
-            per_rank = int(np.ceil(total / world))
+        total = min(n_samples, len(test_ds))
+        per_rank = int(np.ceil(total / world))
+        if world > 1 and hasattr(local_fn, 'local_records') and dist.get_backend() == 'nccl':
+            # product path: the shard's records never leave the device before the all-gather; ONE D2H copy afterwards
+            rec, rn, _, _ = local_fn.local_records(model)
             dev = next(model.parameters()).device
-            mols = gather_mols(local_mols, per_rank, N, dev)
+            if rec is None:
+                rec = torch.zeros(0, D.record_bytes(rn), dtype=torch.uint8, device=dev)
+            if rec.shape[0] < per_rank:                 # short last shard: empty records (n = 0) keep the gather uniform
+                rec = torch.cat([rec, torch.zeros(per_rank - rec.shape[0], rec.shape[1], dtype=torch.uint8, device=dev)])
+            mols = [m for m in D.unpack_records(D.gather_records(rec), rn) if m[1].shape[0] > 0]
+        else:
+            local_mols, _, _ = local_fn(model)
+            if world == 1:
+                mols = local_mols
+            else:
+                dev = next(model.parameters()).device
+                mols = gather_mols(local_mols, per_rank, N, dev)
         # ground truth of ALL samples, same permutation as the local driver (sampling.py:387-391)
         g = torch.Generator().manual_seed(42)
         perm = torch.randperm(len(test_ds), generator=g)[:n_samples]

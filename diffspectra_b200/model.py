@@ -185,7 +185,8 @@ class _B200Denoiser(nn.Module):
         self._engine = None
         self._weights_key = None
         self._weights_fp = None
-        self._plan_cache = {}
+        self._plan_cache = {}          # identity key -> (mask tensor kept alive, plan)
+        self._plan_content = {}        # (n_atoms bytes, N, device) -> plan
         self._ctx_cache = (None, None)
 
     # ------------------------------------------------------------------ checkpoint ingestion
@@ -249,6 +250,7 @@ class _B200Denoiser(nn.Module):
             self._engine = Engine(device, mode=self.precision, spectra_version=self.spectra_version, model_kind=self.MODEL_KIND)
             self._weights_key = None
             self._plan_cache = {}
+            self._plan_content = {}
             self._ctx_cache = (None, None)
         key = self._params_key()
         stale = key != self._weights_key                 # load_state_dict / optimizer step / .to() happened
@@ -275,31 +277,47 @@ class _B200Denoiser(nn.Module):
         return self
 
     def plan_for(self, node_mask):
-        """Plan keyed by the mask tensor's identity; building it costs one small D2H copy (n_atoms)."""
-        key = (node_mask.data_ptr(), node_mask._version, tuple(node_mask.shape))
-        plan = self._plan_cache.get(key)
+        """Molecule plan of a node mask.  Two-level cache:
+        * identity fast path (a denoiser call per step passes the SAME tensor 1000 times): keyed by
+          (data_ptr, _version, shape, device) and the entry HOLDS the mask tensor, so its address cannot be handed to a
+          different mask by the caching allocator while the entry lives (round r's mask used to be freed when round r+1
+          rebound it, and round r+2 could get the same address back -> a stale plan for different molecules);
+        * content key (tuple of atom counts, N): a new mask object with the same atom counts re-uses the plan, any other
+          content builds a new one.  Costs one small D2H copy per NEW mask object (once per sampling round)."""
+        key = (node_mask.data_ptr(), node_mask._version, tuple(node_mask.shape), str(node_mask.device))
+        hit = self._plan_cache.get(key)
+        if hit is not None and hit[0] is node_mask:
+            return hit[1]
+        nm = node_mask.reshape(node_mask.shape[0], -1)
+        n_atoms = nm.sum(dim=1).round().to(torch.int32).cpu().numpy()
+        # valid atoms must be a prefix (sampling.py:432-434)
+        if not bool((nm[:, :1] > 0).all()) or not bool(((nm[:, 1:] - nm[:, :-1]) <= 0).all()):
+            raise ValueError('%s expects prefix node masks (first n atoms valid) as built by sampling.py:432-434'
+                             % type(self).__name__)
+        ckey = (n_atoms.tobytes(), int(nm.shape[1]), str(node_mask.device))
+        plan = self._plan_content.get(ckey)
         if plan is None:
-            nm = node_mask.reshape(node_mask.shape[0], -1)
-            n_atoms = nm.sum(dim=1).round().to(torch.int32).cpu().numpy()
-            # valid atoms must be a prefix (sampling.py:432-434)
-            if not bool((nm[:, :1] > 0).all()) or not bool(((nm[:, 1:] - nm[:, :-1]) <= 0).all()):
-                raise ValueError('%s expects prefix node masks (first n atoms valid) as built by sampling.py:432-434'
-                                 % type(self).__name__)
             plan = self._engine.plan(n_atoms, nm.shape[1])
-            if len(self._plan_cache) > 8:
-                self._plan_cache.clear()
-            self._plan_cache[key] = plan
+            if len(self._plan_content) >= 8:
+                self._plan_content.clear()
+            self._plan_content[ckey] = plan
+        if len(self._plan_cache) >= 8:
+            self._plan_cache.clear()
+        self._plan_cache[key] = (node_mask, plan)
         return plan
 
     def context_embedding(self, context):
         """cond_lin(SpecFormer(context)), cached while the same spectra tensors are passed (they are constant
-        across the 1000 steps of a sampling round; the reference recomputes them every call)."""
-        ts = context if isinstance(context, (list, tuple)) else [context]
+        across the 1000 steps of a sampling round; the reference recomputes them every call).  The cache entry holds
+        the tensors themselves (identity compare + version), so a recycled address can never alias an old entry."""
+        ts = list(context) if isinstance(context, (list, tuple)) else [context]
         key = tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in ts)
-        if self._ctx_cache[0] != key:                    # a new sampling round: also the point where weights are re-verified
+        held = self._ctx_cache[0]
+        same = held is not None and held[0] == key and len(held[1]) == len(ts) and all(a is b for a, b in zip(held[1], ts))
+        if not same:                                     # a new sampling round: also the point where weights are re-verified
             self._ctx_cache = (None, None)
             eng = self.engine(verify=True)
-            self._ctx_cache = (key, eng.context_embedding(context))
+            self._ctx_cache = ((key, ts), eng.context_embedding(context))
         return self._ctx_cache[1]
 
     # ------------------------------------------------------------------ reference interface

@@ -139,6 +139,31 @@ def mol_process(one_hot, x, formal_charges, n_nodes, edge_types=None):
     return mols
 
 
+def molecule_records(x_node, x_edge, node_mask, model, rec_n=None):
+    """Device post_process + mol_process in one kernel (ds_molecule_records): uint8 [B, record_bytes(rec_n)] on the
+    device (layout: distributed.record_bytes)."""
+    net = _unwrap(model)
+    eng = net.engine(x_node.device)
+    return eng.molecule_records(net.plan_for(node_mask), x_node, x_edge, rec_n)
+
+
+class _HostRecords:
+    """Asynchronous D2H copy of a record tensor into pinned memory; `.mols()` waits for it and converts — so the host
+    conversion of one sampling round overlaps the GPU work of the next."""
+
+    def __init__(self, rec, rec_n):
+        self.rec_n = rec_n
+        self.host = torch.empty(rec.shape, dtype=torch.uint8, pin_memory=True)
+        self.host.copy_(rec, non_blocking=True)
+        self.ev = torch.cuda.Event()
+        self.ev.record()
+
+    def mols(self):
+        from .distributed import unpack_records
+        self.ev.synchronize()
+        return unpack_records(self.host, self.rec_n)
+
+
 def make_masks(n_nodes, device, max_n_nodes=None):
     """node_mask [B,N,1], edge_mask [B*N*N,1] — sampling.py:429-439, vectorised."""
     n = torch.as_tensor(n_nodes, dtype=torch.long)
@@ -149,43 +174,125 @@ def make_masks(n_nodes, device, max_n_nodes=None):
     return node_mask.unsqueeze(2).to(device), edge_mask.view(-1, 1).to(device)
 
 
+def _parse_normalize_factors(v):
+    if isinstance(v, str):
+        return [int(t) for t in v.split(',')]
+    return [int(t) for t in v]
+
+
+def check_eval_config(config):
+    """post_process / the record kernels bake in the shipped data configuration (configs/diffspectra_qm9s.py:23-30,
+    50-51; utils.py:71-105): anything else must fail loudly instead of producing wrong atom types / charges / bonds."""
+    d, m = config.data, config.model
+    problems = []
+    if int(d.atom_types) != 5:
+        problems.append('data.atom_types=%r (need 5)' % (d.atom_types,))
+    if not bool(m.include_fc_charge):
+        problems.append('model.include_fc_charge=False (need True)')
+    if not bool(d.compress_edge):
+        problems.append('data.compress_edge=False (need True)')
+    if not bool(d.centered):
+        problems.append('data.centered=False (need True)')
+    if _parse_normalize_factors(m.normalize_factors) != [1, 4, 4, 1]:
+        problems.append("model.normalize_factors=%r (need '1, 4, 4, 1')" % (m.normalize_factors,))
+    if not bool(config.pred_edge) or int(m.edge_ch) != 2:
+        problems.append('pred_edge / edge_ch (need True / 2)')
+    if problems:
+        raise ValueError('the B200 eval driver implements the shipped QM9S data configuration only: ' + '; '.join(problems))
+
+
+def stage_round(test_ds, ids, keys):
+    """Host staging of one sampling round (reference: the per-item loop of sampling.py:397-427).  Returns
+    (n_nodes list, [spectra tensor per key, each [B,1,L]], ground-truth positions list, rdmol list).
+
+    Fast path: a PyG ``InMemoryDataset`` (what datasets/qm9s_dataset.py:QM9S is) keeps every attribute of all items
+    concatenated in ``_data`` with a ``slices`` table; when each item owns exactly one row of a spectrum the whole batch
+    is ONE index_select per spectrum instead of B item constructions + a B-way torch.stack.  Anything else (a plain
+    list, an unknown dataset class) takes the reference's item-by-item path."""
+    ids = [int(i) for i in ids]
+    data = getattr(test_ds, '_data', None)
+    slices = getattr(test_ds, 'slices', None)
+    if data is not None and slices is not None:
+        try:
+            idx = torch.as_tensor(ids, dtype=torch.long)
+            own = getattr(test_ds, '_indices', None)
+            if own is not None:                            # a subset view (dataset[split]) maps through its index list
+                idx = torch.as_tensor(list(own), dtype=torch.long)[idx]
+            spectra = []
+            for k in keys:
+                sl = torch.as_tensor(slices[k], dtype=torch.long)
+                start, end = sl[idx], sl[idx + 1]
+                if not bool((end - start == 1).all()):
+                    raise ValueError('spectrum rows per item != 1')
+                spectra.append(getattr(data, k).index_select(0, start).unsqueeze(1))
+            nsl = torch.as_tensor(slices['num_atom'], dtype=torch.long)
+            n_nodes = [int(v) for v in getattr(data, 'num_atom').index_select(0, nsl[idx]).reshape(-1)]
+            psl = torch.as_tensor(slices['pos'], dtype=torch.long)
+            pos_all = getattr(data, 'pos')
+            tpos = [pos_all[int(a):int(b)] for a, b in zip(psl[idx], psl[idx + 1])]
+            rd = getattr(data, 'rdmol', None)
+            rdm = [rd[int(i)] if isinstance(rd, (list, tuple)) else None for i in idx]
+            return n_nodes, spectra, tpos, rdm
+        except (KeyError, AttributeError, ValueError, IndexError, TypeError):
+            pass
+    mols = [test_ds[i] for i in ids]
+    n_nodes = [int(m.num_atom.item()) if torch.is_tensor(m.num_atom) else int(m.num_atom) for m in mols]
+    spectra = [torch.stack([getattr(m, k) for m in mols]) for k in keys]
+    return n_nodes, spectra, [m.pos for m in mols], [getattr(m, 'rdmol', None) for m in mols]
+
+
 def get_cond_sampling_eval_fn(config, noise_scheduler, batch_size, n_samples, inverse_scaler, test_ds, eps=1e-3,
                               noise='torch', seed=0, rank=0, world_size=1):
     """Eval driver with the reference's contract (sampling.py:353-468): `sampling_fn(model)` returns
     (processed_mols, sampled_test_pos, sampled_test_rdkit_mols), each truncated to n_samples.
-    With world_size > 1 each rank samples a contiguous shard of the permuted test set (SURVEY.md §8(e));
-    gathering the shards is done by `diffspectra_b200.distributed.gather_records`."""
-    from .sampling import AncestralSampler as _Sampler
+
+    noise='torch' (validation): like the reference, every round is a FULL batch of `batch_size` items of the permuted
+    test set (sampling.py:388-391) and the lists are truncated afterwards, so the torch RNG stream and all shapes are
+    the reference's; the test set must hold ceil(n_samples / batch_size) * batch_size items, as the reference requires.
+    noise='philox' (throughput): exactly n_samples molecules are sampled; with world_size > 1 each rank takes a
+    contiguous shard of them and noise is keyed by the global sample index, so the result does not
+    depend on the sharding.  Gathering the shards is `diffspectra_b200.distributed.gather_records`."""
     device = config.device
     if config.sampling.method != 'ancestral' or config.only_2D:
         raise ValueError('Invalid sampling method!')
+    check_eval_config(config)
     spectra_version = config.data.spectra_version
+    keys = ['uv', 'ir', 'raman'] if spectra_version == 'allspectra' else [spectra_version]
     time_steps = torch.linspace(noise_scheduler.T, eps, config.sampling.steps, device=device)
+    # ONE sampler for every round and every model: its coefficient table (a 1000-iteration host loop) is built once
+    sampler = AncestralSampler(noise_scheduler, time_steps, config.model.pred_data, config.pred_edge,
+                               config.model.self_cond, None, config.eval.sampling_temperature, noise=noise, seed=seed)
 
-    def sampling_fn(model):
+    rec_n = int(getattr(config.data, 'max_node', 0) or 0)
+
+    def _rounds(model, consume):
+        """Runs this rank's rounds; hands every round's DEVICE records [B, record_bytes] to `consume` (after the next
+        round has been enqueued, so whatever `consume` does on the host overlaps GPU work).  Returns the ground truth."""
         model.eval()
-        processed_mols, sampled_test_pos, sampled_test_rdkit_mols = [], [], []
+        sampled_test_pos, sampled_test_rdkit_mols = [], []
         with torch.no_grad():
             torch.manual_seed(42)                      # same spectra selection for every model (sampling.py:387)
-            perm = torch.randperm(len(test_ds))[:n_samples]
+            perm = torch.randperm(len(test_ds))
+            if noise == 'torch':
+                total = min(len(perm), int(np.ceil(n_samples / batch_size)) * batch_size)
+            else:
+                total = min(len(perm), n_samples)
+            perm = perm[:total]
             per_rank = int(np.ceil(len(perm) / world_size))
             mine = perm[rank * per_rank:(rank + 1) * per_rank]
             gid0 = rank * per_rank
+            done = 0
             for r in range(int(np.ceil(len(mine) / batch_size))):
                 ids = mine[r * batch_size:(r + 1) * batch_size]
-                mols = [test_ds[int(i)] for i in ids]
-                n_nodes = [int(m.num_atom.item()) if torch.is_tensor(m.num_atom) else int(m.num_atom) for m in mols]
-                keys = ['uv', 'ir', 'raman'] if spectra_version == 'allspectra' else [spectra_version]
-                ctx = [torch.stack([getattr(m, k) for m in mols]) for k in keys]
+                n_nodes, ctx, tpos, rdm = stage_round(test_ds, ids, keys)
+                sampled_test_pos += tpos
+                sampled_test_rdkit_mols += rdm
+                # pinned staging + asynchronous H2D: the copy does not block the host while the previous round runs
+                ctx = [c.pin_memory().to(device, non_blocking=True) if c.device.type == 'cpu' else c.to(device) for c in ctx]
                 context = ctx if spectra_version == 'allspectra' else ctx[0]
-                for m in mols:
-                    sampled_test_pos.append(m.pos)
-                    sampled_test_rdkit_mols.append(getattr(m, 'rdmol', None))
                 node_mask, edge_mask = make_masks(n_nodes, device)
-                sampler = _Sampler(noise_scheduler, time_steps, config.model.pred_data, config.pred_edge,
-                                   config.model.self_cond, None, config.eval.sampling_temperature, noise=noise, seed=seed,
-                                   gid_base=gid0 + r * batch_size)
-                B, N = len(mols), node_mask.shape[1]
+                sampler.gid_base = gid0 + r * batch_size
+                B, N = len(n_nodes), node_mask.shape[1]
                 if noise == 'philox':
                     # initial state drawn in the kernel too, keyed by the global molecule id: the whole trajectory is
                     # invariant to how the test set is sharded over ranks / rounds
@@ -197,10 +304,33 @@ def get_cond_sampling_eval_fn(config, noise_scheduler, batch_size, n_samples, in
                     ez = torch.randn(B, 2, N, N, device=device).tril(-1)
                     ez = (ez + ez.transpose(-1, -2)).permute(0, 2, 3, 1) * edge_mask.reshape(B, N, N, 1)
                 x_node, x_edge = sampler.sampling(model, z, node_mask, edge_mask, ez, context)
-                pos, one_hot, fc, edge_types = post_process(x_node, 5, True, node_mask, inverse_scaler, x_edge, edge_mask,
-                                                            True, model=model)
-                processed_mols += mol_process(one_hot, pos, fc, n_nodes, edge_types)
-                print('Generate {}, Total {}.'.format(len(processed_mols), n_samples))
-        return processed_mols[:n_samples], sampled_test_pos[:n_samples], sampled_test_rdkit_mols[:n_samples]
+                consume(molecule_records(x_node, x_edge, node_mask, model, max(rec_n, N)), max(rec_n, N))
+                done += B
+                print('Generate {}, Total {}.'.format(done, n_samples))
+        return sampled_test_pos, sampled_test_rdkit_mols
 
+    def sampling_fn(model):
+        processed_mols, pending = [], []
+
+        def consume(rec, rn):
+            pending.append(_HostRecords(rec, rn))       # async D2H now ...
+            while len(pending) > 1:                     # ... conversion of the PREVIOUS round while this one runs
+                processed_mols.extend(pending.pop(0).mols())
+
+        tpos, rdm = _rounds(model, consume)
+        for h in pending:
+            processed_mols.extend(h.mols())
+        return processed_mols[:n_samples], tpos[:n_samples], rdm[:n_samples]
+
+    def local_records(model):
+        """This rank's molecules as ONE device tensor of records (uniform size: record_bytes(max_node)) + the ground
+        truth lists; what `evaluate.get_cond_sampling_eval_fn` all-gathers."""
+        recs = []
+        tpos, rdm = _rounds(model, lambda rec, rn: recs.append((rec, rn)))
+        rn = max([q for _, q in recs] + [1])
+        if any(q != rn for _, q in recs):
+            raise ValueError('rounds produced records of different sizes; set config.data.max_node')
+        return (torch.cat([r for r, _ in recs]) if recs else None), rn, tpos, rdm
+
+    sampling_fn.local_records = local_records
     return sampling_fn

@@ -131,6 +131,16 @@ int ds_post_process(ds_ctx* ctx, const void* plan, int B, int N, int Mn, int Mp,
                     const float* edge_mean, float* pos, int* atom_type, int* formal_charge, float* bond,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Molecule records — mol_process + post_process (sampling.py:12-32,53-97) fused: from the reference-shaped means of the
+ * last step straight to one fixed-size byte record per molecule,
+ *   pos f32[R*3] | atom_type u8[R] | formal_charge i8[R] | bond u8[R*R] | n_atoms u8      (ds_record_bytes(R) = 14 R + R^2 + 1)
+ * R = rec_n >= N (e.g. the data set's max_node, so that rounds with a smaller padded N emit records of one size), with
+ * the same discretisation as ds_post_process; padded atoms / bonds are 0.  records[B * ds_record_bytes(rec_n)] is the unit
+ * of the single D2H copy of the eval driver and of the one all-gather of the multi-GPU path. */
+size_t ds_record_bytes(int rec_n);
+int ds_molecule_records(ds_ctx* ctx, const void* plan, int B, int N, int Mn, int Mp, const float* x_mean,
+                        const float* edge_mean, int rec_n, void* records, size_t records_bytes, void* stream);
+
 /* Test hook: out[M,N] = act(A[M,K] W[N,K]^T + bias + addmat).  use_tensor_cores=1 -> the tcgen05/TMA kernel
  * (bf16 A/W), 0 -> the CUDA-core kernel.  dtype 0 = f32, 1 = bf16; act 0 none, 1 SiLU, 2 tanh, 3 GELU(erf). */
 int ds_gemm(ds_ctx* ctx, int use_tensor_cores, const void* A, int lda, const void* W, int ldw, const float* bias,

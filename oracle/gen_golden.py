@@ -165,6 +165,33 @@ def gen_sampler(R, full=False):
                    os.path.join(OUT, 'sampler_%s_%d.pt' % (version, steps)))
 
 
+def gen_sampler_stat(R, B=128, steps=50, salt=4, seed=42, ctx_seed=56, n_seed=4321, tag=None):
+    """Statistics-sized free-running trajectory (north_star: ">= 99 % of molecules with identical atom types and bond
+    orders, RMSD <= 1e-3 A"): B molecules with QM9S-histogram atom counts, allspectra, the reference AncestralSampler +
+    post_process.  Stored compactly: the final means (fp32) and the discrete molecules as small integers."""
+    ns = R.NoiseScheduleVP('cosine', continuous_beta_0=0.1, continuous_beta_1=20.)
+    version = 'allspectra'
+    m = _model(R, version, salt=salt)
+    n = W.sample_n_atoms(B, seed=n_seed)
+    N = 29
+    nm, em = W.make_masks(n, N)
+    ctx = W.synthetic_spectra(B, version, seed=ctx_seed)
+    sampler = R.AncestralSampler(ns, torch.linspace(ns.T, 1e-3, steps), True, True, True,
+                                 R.get_self_cond_fn(R.config), sampling_temperature=1.0)
+    torch.manual_seed(seed)
+    z = R.mutils.sample_combined_position_feature_noise(B, N, 6, nm)
+    ez = R.mutils.sample_symmetric_edge_feature_noise(B, N, 2, em)
+    with torch.no_grad():
+        x_mean, ex_mean = sampler.sampling(m, z, nm, em, ez, ctx)
+        inv = R.get_data_inverse_scaler(R.config)
+        pos, one_hot, fc, bond = R.post_process(x_mean, 5, True, nm, inv, ex_mean, em, True)
+    iu = torch.triu_indices(N, N, 1)
+    torch.save(dict(version=version, steps=steps, n_atoms=n, N=N, salt=salt, seed=seed, ctx_seed=ctx_seed,
+                    x_mean=x_mean, edge_x_mean_triu=ex_mean[:, iu[0], iu[1]].contiguous(), pos=pos,
+                    atom=one_hot.argmax(-1).to(torch.uint8), fc=fc.squeeze(-1).to(torch.int8), bond=bond.to(torch.uint8)),
+               os.path.join(OUT, tag or 'sampler_stat_%s_%d_b%d.pt' % (version, steps, B)))
+
+
 def gen_noise_kat(R):
     n = torch.tensor([29, 4, 13])
     B, N = 3, 29
@@ -180,6 +207,12 @@ def main():
     R = load_reference()
     if '--only-full' in sys.argv:
         gen_sampler(R, full=True)
+        return
+    if '--only-stat' in sys.argv:        # B=128 x 50 steps (a few minutes of CPU)
+        gen_sampler_stat(R)
+        return
+    if '--only-stat-full' in sys.argv:   # B=32 x 1000 steps (about an hour of CPU)
+        gen_sampler_stat(R, B=32, steps=1000, salt=5, seed=43, ctx_seed=57, n_seed=4322)
         return
     gen_manifest(R)
     gen_schedule(R)

@@ -13,10 +13,9 @@ import zlib
 
 import torch
 
-# atom-count histogram of QM9S (datasets/datasets_config.py:23-25, 'qm9_second_half')
-QM9_N_NODES = {3: 1, 4: 3, 5: 3, 6: 5, 7: 7, 8: 25, 9: 62, 10: 178, 11: 412, 12: 845, 13: 1541, 14: 2587,
-               15: 3865, 16: 5344, 17: 6461, 18: 6695, 19: 6944, 20: 4794, 21: 4962, 22: 1701, 23: 2380,
-               24: 267, 25: 754, 26: 17, 27: 132, 29: 15}
+# the synthetic-input helpers live in the product package (bench.py's CUDA arm may not import oracle/); re-exported here
+# because every test and the golden generator reach them as W.sample_n_atoms / W.synthetic_spectra
+from diffspectra_b200.synthetic import QM9_N_NODES, sample_n_atoms, synthetic_spectra  # noqa: E402,F401
 
 
 def _gen(name, salt):
@@ -65,19 +64,6 @@ def keyed_fill_(state_dict, salt=0, coord_scale=None):
     return state_dict
 
 
-def sample_n_atoms(B, seed=1234, force_first_max=True, max_n=29):
-    """n ~ Categorical(QM9S histogram); molecule 0 forced to max_n so N_pad = 29."""
-    ks = torch.tensor(sorted(QM9_N_NODES.keys()))
-    w = torch.tensor([QM9_N_NODES[int(k)] for k in ks], dtype=torch.float64)
-    g = torch.Generator()
-    g.manual_seed(seed)
-    idx = torch.multinomial(w / w.sum(), B, replacement=True, generator=g)
-    n = ks[idx].clone()
-    if force_first_max:
-        n[0] = max_n
-    return n
-
-
 def make_masks(n_atoms, N=None):
     """node_mask [B,N,1], edge_mask [B*N*N,1] exactly as sampling.py:432-439."""
     B = len(n_atoms)
@@ -89,14 +75,3 @@ def make_masks(n_atoms, N=None):
     diag = ~torch.eye(N, dtype=torch.bool).unsqueeze(0)
     edge_mask = edge_mask * diag
     return node_mask.unsqueeze(2), edge_mask.view(B * N * N, 1)
-
-
-def synthetic_spectra(B, version='allspectra', seed=1235):
-    """log10(1 + 50*U[0,1)) spectra (mirrors datasets/build_dataset.py:142-148); list or tensor like
-    sampling.py:423-427."""
-    g = torch.Generator()
-    g.manual_seed(seed)
-    lens = {'uv': 701, 'ir': 3501, 'raman': 3501}
-    order = ['uv', 'ir', 'raman'] if version == 'allspectra' else [version]
-    out = [torch.log10(1 + 50 * torch.rand(B, 1, lens[k], generator=g)) for k in order]
-    return out if version == 'allspectra' else out[0]

@@ -5,6 +5,8 @@ world_size 2 over gloo must equal world_size 1."""
 import os
 import types
 
+import pytest
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -100,13 +102,70 @@ def test_install_swaps_the_reference_seams():
     fake_run_lib = types.SimpleNamespace(get_cond_sampling_eval_fn=None, NoiseScheduleVP=None)
     E.install(fake_run_lib)
     assert fake_run_lib.NoiseScheduleVP is NoiseScheduleVP
-    cfg = types.SimpleNamespace(data=types.SimpleNamespace(max_node=29, spectra_version='ir'), device='cpu', only_2D=False,
-                                sampling=types.SimpleNamespace(method='ancestral', steps=5),
-                                model=types.SimpleNamespace(pred_data=True, self_cond=True), pred_edge=True,
-                                eval=types.SimpleNamespace(sampling_temperature=1.0))
+    from diffspectra_b200.config import get_config
+    cfg = get_config('ir', device='cpu')
+    cfg.sampling.steps = 5
     ns = NoiseScheduleVP('cosine', continuous_beta_0=0.1, continuous_beta_1=20.)
     fn = fake_run_lib.get_cond_sampling_eval_fn(cfg, ns, 4, 8, None, [_Mol(i) for i in range(9)])
     assert callable(fn)
+    # a data configuration the record / post-process kernels do not implement must be refused, not mis-sampled
+    for key, section, bad in (('normalize_factors', 'model', '1, 2, 2, 1'), ('compress_edge', 'data', False),
+                              ('centered', 'data', False), ('atom_types', 'data', 4), ('include_fc_charge', 'model', False)):
+        cfg2 = get_config('ir', device='cpu')
+        cfg2[section][key] = bad
+        with pytest.raises(ValueError):
+            fake_run_lib.get_cond_sampling_eval_fn(cfg2, ns, 4, 8, None, [_Mol(i) for i in range(9)])
+
+
+def test_stage_round_fast_path_equals_item_loop():
+    """sampling.stage_round: the InMemoryDataset fast path (one index_select per spectrum over the collated storage)
+    returns exactly what the reference's item-by-item loop (sampling.py:397-427) builds."""
+    from diffspectra_b200.sampling import stage_round
+    g = torch.Generator().manual_seed(0)
+    n_items = 12
+    n_at = torch.randint(3, 10, (n_items,), generator=g)
+    off = torch.cat([torch.zeros(1, dtype=torch.long), n_at.cumsum(0)])
+
+    class Item:
+        pass
+
+    class InMem:                                   # the two attributes PyG's InMemoryDataset keeps: _data + slices
+        def __init__(self, indices=None):
+            self._data = types.SimpleNamespace(
+                uv=torch.rand(n_items, 701, generator=torch.Generator().manual_seed(1)),
+                ir=torch.rand(n_items, 3501, generator=torch.Generator().manual_seed(2)),
+                raman=torch.rand(n_items, 3501, generator=torch.Generator().manual_seed(3)),
+                num_atom=n_at.clone(), pos=torch.rand(int(off[-1]), 3, generator=torch.Generator().manual_seed(4)))
+            ar = torch.arange(n_items + 1)
+            self.slices = dict(uv=ar, ir=ar, raman=ar, num_atom=ar, pos=off)
+            self._indices = indices
+
+        def __len__(self):
+            return n_items if self._indices is None else len(self._indices)
+
+        def __getitem__(self, i):
+            j = int(i) if self._indices is None else int(self._indices[int(i)])
+            it = Item()
+            it.uv, it.ir, it.raman = self._data.uv[j:j + 1], self._data.ir[j:j + 1], self._data.raman[j:j + 1]
+            it.num_atom = self._data.num_atom[j]
+            it.pos = self._data.pos[int(off[j]):int(off[j + 1])]
+            it.rdmol = None
+            return it
+
+    for ds in (InMem(), InMem(indices=[7, 2, 9, 0, 11, 4])):
+        ids = [3, 0, 5] if len(ds) < 12 else [10, 1, 7, 3]
+        keys = ['uv', 'ir', 'raman']
+        fast = stage_round(ds, ids, keys)
+        items = [ds[i] for i in ids]
+        assert fast[0] == [int(m.num_atom) for m in items]
+        for k, t in zip(keys, fast[1]):
+            assert t.shape == (len(ids), 1, getattr(items[0], k).shape[-1])
+            assert torch.equal(t, torch.stack([getattr(m, k) for m in items]))
+        assert all(torch.equal(a, m.pos) for a, m in zip(fast[2], items))
+    # a plain list takes the item loop
+    plain = [InMem()[i] for i in range(5)]
+    out = stage_round(plain, [4, 2], ['ir'])
+    assert out[0] == [int(plain[4].num_atom), int(plain[2].num_atom)] and out[1][0].shape == (2, 1, 3501)
 
 
 def test_records_from_mols_roundtrip():

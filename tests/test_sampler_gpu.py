@@ -248,6 +248,71 @@ def test_eval_driver_contract_and_rank_sharding():
     assert same >= n_samples - 1        # identical noise per global molecule id; bf16 tiles cut differently
 
 
+def test_multi_round_driver_never_reuses_a_stale_plan():
+    """Rounds of the SAME shape (B, N) but different atom counts (sampling.py:390-465): the plan / context caches of the
+    model are keyed by tensor identity for speed and must never hand round r's plan to round r+2 when the allocator
+    recycles the freed mask's address.  5 rounds of 8 molecules on ONE model == the same rounds each sampled alone on a
+    FRESH model (Philox noise is keyed by the global sample index, so rank r of 5 is exactly round r)."""
+    from diffspectra_b200.config import get_config
+    from diffspectra_b200.sampling import get_cond_sampling_eval_fn, make_masks
+    cfg = get_config('ir', device='cuda', precision='bf16')
+    cfg.sampling.steps = 4
+    ns = NoiseScheduleVP('cosine', continuous_beta_0=0.1, continuous_beta_1=20.)
+    rounds, batch = 5, 8
+    n_items = rounds * batch
+    torch.manual_seed(42)
+    perm = torch.randperm(n_items)
+    n_list = W.sample_n_atoms(n_items, seed=11, force_first_max=False).clamp(max=28)
+    for r in range(rounds):
+        n_list[int(perm[r * batch])] = 29            # every round pads to N = 29: identical mask shapes
+    ds = [_FakeMol(int(n), 500 + i) for i, n in enumerate(n_list)]
+    model = build_model('ir', salt=3, coord_scale=0.02, precision='bf16')
+    # (a) the cache itself: same-shape masks created and dropped in a loop (what the allocator recycles)
+    for r in range(12):
+        nr = n_list[perm[(r % rounds) * batch:(r % rounds + 1) * batch]]
+        nm, _ = make_masks(nr.tolist(), 'cuda')
+        model.engine('cuda')
+        plan = model.plan_for(nm)
+        assert plan.n_atoms.tolist() == nr.tolist(), (r, plan.n_atoms.tolist(), nr.tolist())
+        del nm, plan
+    # (b) end to end
+    whole = get_cond_sampling_eval_fn(cfg, ns, batch, n_items, None, ds, noise='philox', seed=9)(model)[0]
+    assert len(whole) == n_items
+    for r in range(rounds):
+        fresh = build_model('ir', salt=3, coord_scale=0.02, precision='bf16')
+        part = get_cond_sampling_eval_fn(cfg, ns, batch, n_items, None, ds, noise='philox', seed=9, rank=r, world_size=rounds)(fresh)[0]
+        assert len(part) == batch
+        for k, (a, b) in enumerate(zip(whole[r * batch:(r + 1) * batch], part)):
+            n_true = int(n_list[int(perm[r * batch + k])])
+            assert a[0].shape == (n_true, 3) == b[0].shape
+            assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[0], b[0])
+
+
+def test_molecule_records_kernel_equals_post_process():
+    """ds_molecule_records (post_process + mol_process fused, sampling.py:12-32,53-97) == ds_post_process followed by the
+    eager record packing, byte for byte; records padded to a larger rec_n unpack to the same molecules."""
+    from diffspectra_b200.distributed import pack_records, record_bytes, unpack_records
+    from diffspectra_b200.sampling import make_masks
+    n = torch.tensor([29, 1, 7, 18, 2, 23])
+    B, N = len(n), 29
+    model = build_model('ir', precision='bf16')
+    eng = model.engine('cuda')
+    nm, em = make_masks(n, 'cuda', N)
+    plan = model.plan_for(nm)
+    nm_c, em_c = W.make_masks(n, N)
+    g = torch.Generator().manual_seed(12)
+    x = O.node_noise_from_raw(torch.randn(B, N, 3, generator=g), torch.randn(B, N, 6, generator=g) * 0.3, nm_c).cuda()
+    ex = O.edge_noise_from_raw(torch.randn(B, 2, N, N, generator=g), em_c).cuda()
+    pos, atom, fc, bond = eng.post_process(plan, x, ex)
+    want = pack_records(pos, atom, fc, bond, torch.as_tensor(n, device='cuda'))
+    got = eng.molecule_records(plan, x, ex)
+    assert got.shape == (B, record_bytes(N)) and torch.equal(got, want)
+    big = eng.molecule_records(plan, x, ex, rec_n=40)
+    assert big.shape == (B, record_bytes(40))
+    for a, b in zip(unpack_records(got, N), unpack_records(big, 40)):
+        assert all(torch.equal(u, v) for u, v in zip(a, b))
+
+
 def test_sharded_eval_driver_single_process():
     """diffspectra_b200.evaluate at world_size 1: same result lists as the local driver.  The
     2-GPU NCCL path is exercised by tests/run_eval_sharded.py under torchrun."""
