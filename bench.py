@@ -351,7 +351,9 @@ def run_ours(args):
     n_out = [0]
 
     def api_round(r):
-        mols, tpos, _ = api_fn(model)
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):        # the driver prints progress like the reference does (sampling.py:463);
+            mols, tpos, _ = api_fn(model)                   # stdout carries exactly ONE JSON line
         n_out[0] = len(mols)
         return mols
 

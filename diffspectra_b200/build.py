@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libdiffspectra_b200.so')
-SOURCES = ['api_core.cu', 'api_sampling.cu', 'gemm_tc.cu', 'coord_tc.cu', 'edge_ffn_tc.cu', 'gemm_simt.cu', 'dmt_kernels.cu', 'sampler_kernels.cu',
+SOURCES = ['api_core.cu', 'api_sampling.cu', 'gemm_tc.cu', 'coord_head_tc.cu', 'edge_ffn_tc.cu', 'gemm_simt.cu', 'dmt_kernels.cu', 'sampler_kernels.cu',
            'specformer_kernels.cu', 'weights.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
          '--threads', '0']

@@ -1350,7 +1350,8 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         LAUNCH_CHECK(ctx);
       }
       }
-      DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, se));
+      if (!(kFast && (ctx->fuse_mask & 16)))       // the fused coordinate head computes the pair part of input_lin itself
+        DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, se));
       // skip connection into the edge heads (dmt.py:387-388)
       DS_TRY(linear(ctx, X + 64, 128, bw.edge_w, 64, bw.edge_b, nullptr, 0, reinterpret_cast<AT*>(w.ehid) + 64 + 16 * l,
                     192, AD, Mp, 16, 64, ACT_NONE, se));
@@ -1359,8 +1360,8 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     if (Mp > 0) {
       // ---- equivariant coordinate update (needs both chains)
       if (kFast && (ctx->fuse_mask & 16)) {
-        // whole coordinate head in one kernel: the LN+modulate operand never leaves the SM
-        DS_TRY(coord_fused_launch(ctx, plan, w.ab, w.gp, ada_l, w.pflags, bw.wc1, bw.bc1, bw.wc2, w.wdir, s));
+        // whole coordinate head in one kernel on CTA pairs: G stays in TMEM, the LN+modulate operand in shared memory
+        DS_TRY(coord_head_launch(ctx, plan, X, w.ab, ada_l, w.pflags, bw.we, bw.wc1, bw.bc1, bw.wc2, w.wdir, s));
       } else {
         if (kFast && (ctx->fuse_mask & 32))
           ds_launch(k_coord_ln_async, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const bf16*>(w.ab),

@@ -163,10 +163,12 @@ int denoise_wo_eq_packed(DsContext* ctx, const PackedWeights& pw, const Plan& pl
                          const float* cond_x, const float* cond_e, const float* noise_level, StepRef sr,
                          const float* ctx_emb, float* pred_x, float* pred_e, DenoiseWs& w, cudaStream_t s);
 
-// fused coordinate head of one block (coord_tc.cu): LN+modulate operand built in shared memory -> tcgen05 -> w[d]
-int coord_fused_launch(DsContext* ctx, const Plan& plan, const void* ab, const void* gp, const float* ada_l,
-                       const uint8_t* pflags, const void* wc1, const float* bc1, const float* wc2, float* wdir,
-                       cudaStream_t s);
+// fused coordinate head of one block (coord_head_tc.cu): pair part of input_lin -> LayerNorm + modulate -> coord_mlp ->
+// w[d], on CTA pairs (cta_group::2 MMAs); X = the [dist | e] operand [Mp,128] bf16, ab = hoisted per-atom parts [Mn,512] bf16
+int coord_head_launch(DsContext* ctx, const Plan& plan, const void* X, const void* ab, const float* ada_l, const uint8_t* pflags,
+                      const void* we, const void* wc1, const float* bc1, const float* wc2, float* wdir, cudaStream_t s);
+// one cta_group::2 MMA tile: out[256,256] f32 = A[256,K] W[256,K]^T (test probe of the CTA-pair operand split)
+int umma2_probe_launch(DsContext* ctx, const void* A, const void* W, float* out, int K, cudaStream_t s);
 
 // fused edge-stream update of one block (edge_ffn_tc.cu): residual + LN + modulate -> ff3 -> SiLU -> ff4 -> gated residual
 int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ldx, const float* pn, const float* n2e_b,

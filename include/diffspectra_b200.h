@@ -156,6 +156,19 @@ int ds_gemm_fused(ds_ctx* ctx, int mode, const void* A, int lda, const void* W, 
                   const float* resid, int ldres, void* out, int ldo, void* out2, int ldo2, const float* wc2,
                   const unsigned char* dflags, float* wdir, void* stream);
 
+/* Test hook for the CTA-pair (cta_group::2) tensor-core path: out[256,256] (f32) = A[256,K] W[256,K]^T (bf16, K in
+ * {64,128,192,256}) computed by ONE cluster of two CTAs, each holding 128 rows of A and of W. */
+int ds_umma2_probe(ds_ctx* ctx, const void* A, const void* W, float* out, int K, void* stream);
+
+/* Test hook for the fused coordinate head of one block (models/dmt.py:37-60, csrc/coord_head_tc.cu): for every directed edge
+ * d = (r -> c) of the plan, wdir[d] = mean(tanh(wc2 . SiLU(2 (wc1_half . z + bc1_half))) * [1, adj2d, adjsp]) with
+ * z = modulate(LayerNorm(ab[r][0:256] + ab[c][256:512] + we . X[pair]), ada[mol][1920:2176], ada[mol][2176:2432]).
+ * X[Mp,128], ab[Mn,512], we[256,128], wc1_half[256,256] bf16; ada_block = adaLN table of the block (row stride 19584 floats);
+ * pflags[Mp] adjacency bits; wdir[2 Mp] source-major (d = 2 poff[mol] + r (n-1) + c - (c > r)). */
+int ds_coord_head(ds_ctx* ctx, const void* plan, int B, int N, int Mn, int Mp, const void* X, const void* ab,
+                  const float* ada_block, const unsigned char* pflags, const void* we, const void* wc1_half,
+                  const float* bc1_half, const float* wc2, float* wdir, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

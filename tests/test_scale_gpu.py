@@ -98,9 +98,9 @@ def test_philox_loop_is_sharding_invariant():
 
 
 def test_fused_kernels_match_split_path(monkeypatch):
-    """coord_tc.cu (coordinate head: operand built in shared memory -> tcgen05 -> w; DS_FUSE_MASK bit 4) and
-    edge_ffn_tc.cu (edge stream: LN -> ff3 -> SiLU -> ff4 -> gated residual in one kernel; bit 6) are opt-in
-    alternatives to the split kernels: same denoiser output up to bf16 operand rounding order."""
+    """coord_head_tc.cu (coordinate head on CTA pairs: pair GEMM -> LayerNorm operand in shared memory -> coord_mlp -> w;
+    DS_FUSE_MASK bit 4) and edge_ffn_tc.cu (edge stream: LN -> ff3 -> SiLU -> ff4 -> gated residual in one kernel; bit 6)
+    against the split kernels they replace: same denoiser output up to bf16 operand rounding order."""
     version = 'ir'
     n = W.sample_n_atoms(64, seed=3)
     nm, em, x, ex, cx, cex, nl = _inputs(n, 29, seed=41)
