@@ -52,7 +52,7 @@ SIGNATURES = {
     'ds_record_bytes': (_Z, [_I]),
     'ds_molecule_records': (_I, [_P] + _PLAN + [_P, _P, _I, _P, _Z, _P]),
     'ds_umma2_probe': (_I, [_P, _P, _P, _P, _I, _P]),
-    'ds_coord_head': (_I, [_P] + _PLAN + [_P] * 9 + [_P]),
+    'ds_coord_head': (_I, [_P] + _PLAN + [_P] * 10 + [_P]),
     'ds_gemm': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'ds_gemm_fused': (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
 }

@@ -445,12 +445,15 @@ int ds_umma2_probe(ds_ctx* h, const void* A, const void* W, float* out, int K, v
 
 int ds_coord_head(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp, const void* X, const void* ab, const float* ada_block,
                   const unsigned char* pflags, const void* we, const void* wc1_half, const float* bc1_half, const float* wc2, float* wdir,
-                  void* stream) {
+                  void* scratch, void* stream) {
   CtxFull* c = full(h);
-  DS_CHECK(c && X && ab && ada_block && pflags && we && wc1_half && bc1_half && wc2 && wdir, DS_ERR_INVALID, "ds_coord_head: null argument");
+  DS_CHECK(c && X && ab && ada_block && pflags && we && wc1_half && bc1_half && wc2 && wdir && scratch, DS_ERR_INVALID,
+           "ds_coord_head: null argument");
   Plan plan;
   DS_TRY(make_plan(plan_dev, B, N, Mn, Mp, &plan));
-  return coord_head_launch(c, plan, X, ab, ada_block, pflags, we, wc1_half, bc1_half, wc2, wdir, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DS_TRY(coord_mod_launch(c, B, 1, ada_block, scratch, s));      // bf16 modulate vectors of this one block
+  return coord_head_launch(c, plan, X, ab, scratch, pflags, we, wc1_half, bc1_half, wc2, wdir, s);
 }
 
 }  // extern "C"

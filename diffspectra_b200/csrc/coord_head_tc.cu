@@ -19,15 +19,20 @@
 // tile, and every weight byte read from shared memory feeds 256 rows.
 //
 // Per CTA: 10 warps.
-//   warps 0-3 / 4-7   compute groups: even / odd tiles, one THREAD per directed edge (= TMEM lane).  A tile goes
-//                     G (TMEM) -> pass A: LayerNorm statistics -> pass B: normalise + modulate -> Z (shared, SWIZZLE_128B)
-//                     -> [MMA2 overwrites G's columns] -> epilogue: SiLU, 3 dot products, tanh, adjacency mean -> w[d].
-//                     While one group runs its epilogue the other builds the next tile (two TMEM stages of 256 columns).
+//   warps 0-7         compute: TWO threads per directed edge (= TMEM lane; warps w and w + 4 share a lane quadrant and split
+//                     the 256 channels).  Software pipeline over the tiles: pass A(t) (y = G + A + B, LayerNorm statistics; y
+//                     stays in registers as packed bf16) -> epilogue(t-1) (SiLU, 3 dot products, tanh, adjacency mean -> w[d])
+//                     -> pass B(t) (normalise + modulate -> operand tile Z in shared memory, SWIZZLE_128B) -> MMA2(t) overwrites
+//                     G's TMEM columns.  Two TMEM stages of 256 columns: MMA1(t+1) runs under pass B(t), MMA2(t) under pass A(t+1).
 //   warp 8            loader: weights once; per tile the X tile (TMA, counted on the leader's barrier) and the "window":
-//                     the lane-varying halves of the `ab` rows of up to 56 consecutive atoms starting at the tile's first
-//                     atom (TMA, swizzled, so that 32 lanes reading 32 different atoms do not bank-conflict).
+//                     the lane-varying halves of the `ab` rows of up to 48 consecutive atoms starting at the tile's first
+//                     atom (TMA, swizzled, so that 32 lanes reading 32 different atoms do not bank-conflict); atoms beyond
+//                     the window (runs of tiny molecules) are read from global memory.
 //   warp 9            TMEM owner; in the leader CTA also the MMA issuer for both CTAs.
 // Every mbarrier wait is bounded: a protocol error traps with a message instead of hanging the GPU.
+#include <stdlib.h>
+#include <string.h>
+
 #include "kernels.cuh"
 #include "ptx_sm100.cuh"
 
@@ -42,15 +47,16 @@ constexpr int OFF_WE = 4 * kKb;          // input_lin[e | dist] rows [128 rank, 
 constexpr int OFF_Z = 6 * kKb;           // operand tile of MMA2: 4 k-blocks
 constexpr int OFF_X = 10 * kKb;          // operand tile of MMA1: 2 k-blocks
 constexpr int OFF_WIN = 12 * kKb;        // 4 boxes of 56 atoms x 64 channels
-constexpr int OFF_TAB = OFF_WIN + 4 * kWinBox;   // [256] float4: coord_mlp.2 rows + coord_mlp.0 bias per column pair
-constexpr int OFF_BAR = OFF_TAB + 4096;
+constexpr int OFF_TAB = OFF_WIN + 4 * kWinBox;   // [128] uint4, one per column pair: bf16x2 of coord_mlp.2 rows 0, 1, 2 and of the coord_mlp.0 bias
+constexpr int OFF_STAT = OFF_TAB + 2048;         // [2][128] float2 LayerNorm partials of the two channel halves
+constexpr int OFF_BAR = OFF_STAT + 2048;
 constexpr int kSmem = OFF_BAR + 256;
-constexpr int kThreads = 320;
+constexpr int kThreads = 512;             // 8 build warps, 4 epilogue warps, loader, MMA issuer, 2 idle (register donors)
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 struct CoordHeadArgs {
   const bf16* ab;              // [Mn,512]  A = cols 0..255 (with input_lin.bias), B = cols 256..511
-  const float* ada;            // adaLN table pre-offset to block + ADA_COORD: shift [256] | scale [256]; row stride ADA_LD
+  const bf16* cmod;            // [B][512] modulate vectors of this block as bf16: shift [256] | 1 + scale [256] (k_coord_mod)
   const uint8_t* pflags;       // [Mp] adjacency bits of the pair (bit 0 adj2d, bit 1 adjsp)
   const uint32_t* pair_info;   // mol << 12 | i << 6 | j
   const int2* pair_rows;       // atom rows of (i, j)
@@ -60,14 +66,16 @@ struct CoordHeadArgs {
   const float* wc2;            // coord_mlp.2 [3,256]
   float* wdir;                 // [2 Mp] per directed edge, source-major
   int Mp;
+  long long* dbg;              // optional [8 x tiles of block 0] clock stamps of thread 0 (DS_COORD_DBG), else null
 };
 
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
-
-// bounded wait: tag identifies the barrier in the message
+// bounded wait: tag identifies the barrier in the message.  CTA-scope acquire on purpose: a cluster-scope acquire compiles to
+// TRYWAIT + CCTL.IVALL (the whole L1 is invalidated at every successful wait; measured: 30 % of the kernel's stall samples and
+// every per-atom row re-fetched from L2).  What the waits protect is TMEM, TMA-written shared memory or operand tiles read
+// by the tensor core, none of which lives in L1; the remote arrivals carry release.cluster.
 __device__ __forceinline__ void wait_guard(uint64_t* bar, uint32_t parity, int tag, int it) {
   uint32_t spins = 0;
-  while (!ptx::mbar_try_wait_cluster(bar, parity)) {
+  while (!ptx::mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 24)) {
       printf("coord_head_kernel: wait timeout tag=%d it=%d block=%d thread=%d parity=%u\n", tag, it, blockIdx.x, threadIdx.x, parity);
       __trap();
@@ -95,39 +103,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// y[32] = G (TMEM chunk) + uniform row chunk (global) + lane-varying row chunk (window or global) for channels [c0, c0+32)
-__device__ __forceinline__ void load_y32(uint32_t t_addr, int c0, const bf16* urow, const bf16* vrow_g, const uint8_t* win, int wr,
-                                         bool in_win, float (&y)[32]) {
-  uint4 u[4], v[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) u[q] = ldg128(urow + c0 + q * 8);
-  if (in_win) {
-    const uint8_t* wb = win + (c0 >> 6) * kWinBox + wr * 128;
-    const int ch0 = (c0 & 63) >> 3;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const uint4*>(wb + (((ch0 + q) ^ (wr & 7)) << 4));
-  } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = ldg128(vrow_g + c0 + q * 8);
-  }
-  uint32_t acc[32];
-  ptx::tmem_ld32_sync(t_addr + c0, acc);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float uf[8], vf[8];
-    unpack8(u[q], uf);
-    unpack8(v[q], vf);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) y[q * 8 + k] = __uint_as_float(acc[q * 8 + k]) + (uf[k] + vf[k]);
-  }
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
                   const __grid_constant__ CUtensorMap tmWc1, const __grid_constant__ CUtensorMap tmAB, CoordHeadArgs a) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
-  float4* swc2 = reinterpret_cast<float4*>(smem + OFF_TAB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* wl_full = bars + 0;      // local: this CTA's weight halves have landed (tx)
   uint64_t* w_ready = bars + 1;      // leader: both CTAs' weights are in place (2 arrivals)
@@ -146,7 +126,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int n_tiles = (a.Mp + TM - 1) / TM;
   const int my_n = (n_tiles - cid + ncl - 1) / ncl;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 12 && lane == 0) {
     if (ptx::smem_u32(smem) & 1023u) __trap();
     ptx::prefetch_tmap(&tmX);
     ptx::prefetch_tmap(&tmWe);
@@ -159,17 +139,18 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&g_full[i], 1);
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&tmem_free[i], 2);
+      ptx::mbar_init(&tmem_free[i], 8);       // one arrival per epilogue warp of both CTAs
     }
     ptx::mbar_init(win_full, 1);
     ptx::mbar_init(win_free, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 9) ptx::tmem_alloc_2sm<512>(tmem_slot);
-  if (threadIdx.x < 256) {     // per column PAIR (2p, 2p+1): [2p] = (w0, w0', w1, w1'), [2p+1] = (w2, w2', bias, bias')
-    const int c2 = threadIdx.x & ~1;
-    swc2[threadIdx.x] = (threadIdx.x & 1) ? make_float4(a.wc2[512 + c2], a.wc2[513 + c2], a.bc1[c2], a.bc1[c2 + 1])
-                                          : make_float4(a.wc2[c2], a.wc2[c2 + 1], a.wc2[256 + c2], a.wc2[257 + c2]);
+  if (warp == 13) ptx::tmem_alloc_2sm<512>(tmem_slot);
+  if (threadIdx.x < 128) {       // epilogue table: the load/store return path (128 B/clk) is this kernel's scarcest resource and the
+    const int c = 2 * threadIdx.x;   // table is read once per (row, column): bf16 pairs halve those bytes
+    reinterpret_cast<uint4*>(smem + OFF_TAB)[threadIdx.x] =
+        make_uint4(pack2(a.wc2[c], a.wc2[c + 1]), pack2(a.wc2[256 + c], a.wc2[257 + c]), pack2(a.wc2[512 + c], a.wc2[513 + c]),
+                   pack2(a.bc1[c], a.bc1[c + 1]));
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -178,8 +159,9 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  if (warp == 8) {
+  if (warp == 12) {
     // ===================== loader =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(wl_full, 6 * kKb);
       for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_WC1 + kb * kKb, &tmWc1, wl_full, kb * 64, static_cast<int>(rank) * 128);
@@ -199,8 +181,9 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int b = 0; b < 4; ++b) ptx::tma_load_2d(smem + OFF_WIN + b * kWinBox, &tmAB, win_full, (rank ? 0 : 256) + 64 * b, a_lo);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ===================== MMA issuer (leader CTA, one thread, for both CTAs) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, 256);
       wait_guard(w_ready, 0, 4, 0);
@@ -213,8 +196,8 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         bool progressed = false;
         if (next1 < my_n && next1 <= next2 + 1) {
           const int s = next1 & 1;
-          const bool free_ok = next1 < 2 || ptx::mbar_try_wait_cluster(&tmem_free[s], ((next1 >> 1) - 1) & 1);
-          if (free_ok && ptx::mbar_try_wait_cluster(x_full, next1 & 1)) {
+          const bool free_ok = next1 < 2 || ptx::mbar_try_wait(&tmem_free[s], ((next1 >> 1) - 1) & 1);
+          if (free_ok && ptx::mbar_try_wait(x_full, next1 & 1)) {
             ptx::tc_fence_after();
             const uint32_t d = tmem_base + static_cast<uint32_t>(s * 256);
 #pragma unroll
@@ -228,7 +211,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             progressed = true;
           }
         }
-        if (next2 < next1 && ptx::mbar_try_wait_cluster(z_full, next2 & 1)) {
+        if (next2 < next1 && ptx::mbar_try_wait(z_full, next2 & 1)) {
           ptx::tc_fence_after();
           const int s = next2 & 1;
           const uint32_t d = tmem_base + static_cast<uint32_t>(s * 256);
@@ -249,121 +232,208 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
     }
-  } else {
-    // ===================== compute groups: one thread per directed edge =====================
-    const int g = warp >> 2, wq = warp & 3, r = wq * 32 + lane;     // r = row inside the tile = TMEM lane
+  } else if (warp < 8) {
+    // ===================== build warps: TWO threads per directed edge (128 channels each) =====================
+    //   pass A(t)   y = G + A + B for the thread's 128 channels -> LayerNorm partial statistics; y stays in REGISTERS as packed
+    //               bf16 (64 registers), so neither G, nor the window, nor the per-atom rows are needed again
+    //   pass B(t)   normalise + modulate from the registers -> operand tile Z -> MMA2(t)
+    // and straight on to tile t+1 while the epilogue warps drain tile t: the build is bound by TMEM reads, the load/store
+    // return path and issue slots, the epilogue by MUFU.TANH, so the two overlap on one SM.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    const int hf = warp >> 2, wq = warp & 3, r = wq * 32 + lane;     // r = row inside the tile = TMEM lane; hf = channel half
+    const int cb = hf * 128;
     const uint32_t z_full_leader = ptx::mapa(ptx::smem_u32(z_full), 0);
+    float2* sstat = reinterpret_cast<float2*>(smem + OFF_STAT);      // [2][128] (sum, sum of squares) of each channel half
     uint8_t* zbuf = smem + OFF_Z;
     const uint8_t* win = smem + OFF_WIN;
-    for (int it = g; it < my_n; it += 2) {
-      const int s = g;
-      const uint32_t sphase = (it >> 1) & 1;
+    const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+#define DS_STAMP(k) do { if (stamp) a.dbg[it * 8 + (k)] = clock64(); } while (0)
+    for (int it = 0; it < my_n; ++it) {
+      DS_STAMP(0);
+      uint32_t yreg[64];          // the thread's 128 channels of y, packed bf16 pairs
+      const int s = it & 1;
+      const int p0 = (cid + it * ncl) * TM;
+      const int p = p0 + r;
+      const int pc = p < a.Mp ? p : a.Mp - 1;
+      const int2 rows = __ldg(a.pair_rows + pc);
+      const int mol = __ldg(a.pair_info + pc) >> 12;
+      const int a_lo = __ldg(&a.pair_rows[min(p0, a.Mp - 1)].x);
+      const bf16* cm = a.cmod + static_cast<size_t>(mol) * 512 + cb;
+      // rank 0: edge i -> j: y = A[i] + B[j] + G;   rank 1: edge j -> i: y = A[j] + B[i] + G.  The atom that is (nearly)
+      // uniform over the lanes of a warp is i, the lane-varying one j: its half-row comes from the window.
+      const bf16* urow = a.ab + static_cast<size_t>(rows.x) * 512 + (rank ? 256 : 0) + cb;
+      const bf16* vrow = a.ab + static_cast<size_t>(rows.y) * 512 + (rank ? 0 : 256) + cb;
+      const int wr = rows.y - a_lo;
+      const bool in_win = wr >= 0 && wr < kWinRows;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(s * 256 + cb);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(urow));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(urow + 64));
+      wait_guard(&g_full[s], (it >> 1) & 1, 5, it);
+      ptx::tc_fence_after();
+      DS_STAMP(1);
+      wait_guard(win_full, it & 1, 6, it);
+      DS_STAMP(2);
+      // ---- pass A: chunks of 16 channels; the TMEM load of chunk c+1 is in flight while chunk c is consumed
+      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
+      uint32_t accb[2][16];
+      ptx::tmem_ld16_nowait(t_addr, accb[0]);
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t (&acc)[16] = accb[(c0 >> 4) & 1];
+        uint4 u[2], v[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) u[q] = ldg128(urow + c0 + q * 8);
+        if (in_win) {
+          const uint8_t* wb = win + ((cb + c0) >> 6) * kWinBox + wr * 128;
+          const int ch0 = ((cb + c0) & 63) >> 3;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) v[q] = *reinterpret_cast<const uint4*>(wb + (((ch0 + q) ^ (wr & 7)) << 4));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) v[q] = ldg128(vrow + c0 + q * 8);
+        }
+        ptx::tmem_wait_ld16(acc);
+        if (c0 + 16 < 128) ptx::tmem_ld16_nowait(t_addr + c0 + 16, accb[((c0 >> 4) + 1) & 1]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          // A + B as packed bf16 adds (both operands are bf16 already), then fp32: + G, statistics
+          const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u[q]);
+          const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v[q]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 ab2 = __hadd2(u2[k], v2[k]);
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(&ab2);
+            const float2 y2 = fadd2(make_float2(__uint_as_float(acc[q * 8 + 2 * k]), __uint_as_float(acc[q * 8 + 2 * k + 1])),
+                                    make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)));
+            sum2 = fadd2(sum2, y2);
+            sq2 = ffma2(y2, y2, sq2);
+            yreg[(c0 >> 1) + q * 4 + k] = pack2(y2.x, y2.y);
+          }
+        }
+      }
+      sstat[hf * 128 + r] = make_float2(sum2.x + sum2.y, sq2.x + sq2.y);
+      // the modulate vectors of this thread's channels are wanted by pass B
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 64));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 256));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 320));
+      ptx::tc_fence_before();            // this thread's reads of G precede the MMA2 that overwrites those columns
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) ptx::mbar_arrive(win_free);          // every thread is done with the window
+      const float2 mine = sstat[hf * 128 + r], other = sstat[(hf ^ 1) * 128 + r];
+      const float mean = (mine.x + other.x) * (1.0f / 256.0f);
+      const float is = rsqrtf(fmaxf((mine.y + other.y) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-6f);
+      DS_STAMP(3);
+      // the operand buffer is free once MMA2 of the previous tile has completed
+      if (it >= 1) wait_guard(&acc_full[s ^ 1], ((it - 1) >> 1) & 1, 7, it);
+      DS_STAMP(4);
+      // ---- pass B: normalise + modulate from the registers -> bf16 -> SWIZZLE_128B K-major operand row
+      const float nm = -mean * is;
+      const float2 is2 = make_float2(is, is), nm2 = make_float2(nm, nm);
+      // z = LN(y) (1 + scale) + shift with the modulate vectors as bf16 pairs (half the load bytes of the fp32 table) and the
+      // modulate itself as ONE packed bf16 fma per channel pair (fp32 inside, rounded once)
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        uint4 shq[8], scq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          shq[q] = ldg128(cm + hb * 64 + q * 8);
+          scq[q] = ldg128(cm + 256 + hb * 64 + q * 8);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const __nv_bfloat162* sh2 = reinterpret_cast<const __nv_bfloat162*>(&shq[q]);
+          const __nv_bfloat162* sc2 = reinterpret_cast<const __nv_bfloat162*>(&scq[q]);
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t w = yreg[hb * 32 + q * 4 + k];
+            const float2 n2 = ffma2(make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)), is2, nm2);
+            const __nv_bfloat162 z2 = __hfma2(__floats2bfloat162_rn(n2.x, n2.y), sc2[k], sh2[k]);
+            o[k] = *reinterpret_cast<const uint32_t*>(&z2);
+          }
+          *reinterpret_cast<uint4*>(zbuf + (2 * hf + hb) * kKb + r * 128 + ((q ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      ptx::fence_proxy_async_smem();     // operand row visible to the tensor core
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) ptx::mbar_arrive_cluster(z_full_leader);
+      DS_STAMP(5);
+    }
+  } else if (warp < 12) {
+    // ===================== epilogue warps: ONE thread per directed edge, all 256 columns =====================
+    //   u = SiLU(2 (acc + b/2)) ; s_o = wc2[o] . u ; w = mean(tanh(s) * [1, adj2d, adjsp])          (MUFU.TANH-bound)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    const int wq = warp & 3, r = wq * 32 + lane;
+    const uint4* stab = reinterpret_cast<const uint4*>(smem + OFF_TAB);
+    for (int it = 0; it < my_n; ++it) {
+      const int s = it & 1;
       const int p0 = (cid + it * ncl) * TM;
       const int p = p0 + r;
       const bool ok = p < a.Mp;
       const int pc = ok ? p : a.Mp - 1;
-      const int2 rows = __ldg(a.pair_rows + pc);
       const uint32_t info = __ldg(a.pair_info + pc);
       const int mol = info >> 12, ai = (info >> 6) & 63, aj = info & 63;
-      const int a_lo = __ldg(&a.pair_rows[min(p0, a.Mp - 1)].x);
       const int nat = __ldg(a.n_atoms + mol), pb = __ldg(a.poff + mol);
       const uint8_t fl = __ldg(a.pflags + pc);
-      const float* ar = a.ada + static_cast<size_t>(mol) * ADA_LD;
-      // rank 0: edge i -> j: y = A[i] + B[j] + G;   rank 1: edge j -> i: y = A[j] + B[i] + G.  The atom that is (nearly)
-      // uniform over the lanes of a warp is i, the lane-varying one j: its half-row comes from the window.
-      const bf16* urow = a.ab + static_cast<size_t>(rows.x) * 512 + (rank ? 256 : 0);
-      const bf16* vrow = a.ab + static_cast<size_t>(rows.y) * 512 + (rank ? 0 : 256);
-      const int wr = rows.y - a_lo;
-      const bool in_win = wr >= 0 && wr < kWinRows;
       const size_t d_out = static_cast<size_t>(2) * pb + (rank ? static_cast<size_t>(aj) * (nat - 1) + ai : static_cast<size_t>(ai) * (nat - 1) + (aj - 1));
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(s * 256);
-
-      wait_guard(&g_full[s], sphase, 5, it);
-      ptx::tc_fence_after();
-      // a parity wait may run at most one phase ahead of the barrier: the window of tile it-1 must have been consumed (hence
-      // landed) before win_full can be asked about tile it
-      if (it >= 1) wait_guard(win_free, (it - 1) & 1, 9, it);
-      wait_guard(win_full, it & 1, 6, it);
-      // ---- pass A: LayerNorm statistics of y = G + A + B over the 256 channels (thread-local)
-      float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32) {
-        float y[32];
-        load_y32(t_addr, c0, urow, vrow, win, wr, in_win, y);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          sum += y[k];
-          sq = fmaf(y[k], y[k], sq);
-        }
-      }
-      const float mean = sum * (1.0f / 256.0f);
-      const float is = rsqrtf(fmaxf(sq * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-6f);
-      const float nm = -mean * is;
-      // the operand buffer is free once MMA2 of the previous tile (the other group's stage) has completed
-      if (it >= 1) wait_guard(&acc_full[s ^ 1], ((it - 1) >> 1) & 1, 7, it);
-      // ---- pass B: normalise, modulate, bf16, SWIZZLE_128B K-major operand row
-#pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32) {
-        float y[32];
-        load_y32(t_addr, c0, urow, vrow, win, wr, in_win, y);
-        uint8_t* zrow = zbuf + (c0 >> 6) * kKb + r * 128;
-        const int ch0 = (c0 & 63) >> 3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 sh0 = ldg128f(ar + c0 + q * 8), sh1 = ldg128f(ar + c0 + q * 8 + 4);
-          const float4 sc0 = ldg128f(ar + 256 + c0 + q * 8), sc1 = ldg128f(ar + 256 + c0 + q * 8 + 4);
-          const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-          const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-          float z[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) z[k] = fmaf(fmaf(y[q * 8 + k], is, nm), 1.0f + scv[k], shv[k]);
-          *reinterpret_cast<uint4*>(zrow + (((ch0 + q) ^ (r & 7)) << 4)) =
-              make_uint4(pack2(z[0], z[1]), pack2(z[2], z[3]), pack2(z[4], z[5]), pack2(z[6], z[7]));
-        }
-      }
-      ptx::tc_fence_before();            // this thread's reads of G precede the MMA2 that overwrites those columns
-      ptx::fence_proxy_async_smem();     // operand row visible to the tensor core
-      group_sync(g);
-      if (r == 0) {
-        ptx::mbar_arrive(win_free);
-        ptx::mbar_arrive_cluster(z_full_leader);
-      }
-      // ---- epilogue: u = SiLU(2 (acc + b/2)) ; s_o = wc2[o] . u ; w = mean(tanh(s) * [1, adj2d, adjsp])
-      wait_guard(&acc_full[s], sphase, 8, it);
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(s * 256);
+      wait_guard(&acc_full[s], (it >> 1) & 1, 8, it);
       ptx::tc_fence_after();
       float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0;
-#pragma unroll 1
-      for (int c = 0; c < 256; c += 32) {
-        uint32_t acc[32];
-        ptx::tmem_ld32_sync(t_addr + c, acc);
+      uint32_t eacc[2][16];
+      ptx::tmem_ld16_nowait(t_acc, eacc[0]);
+#pragma unroll 2
+      for (int c = 0; c < 256; c += 16) {
+        uint32_t (&acc)[16] = eacc[(c >> 4) & 1];
+        uint4 tb[8];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float4 wa = swc2[c + i], wb = swc2[c + i + 1];
-          const float2 h = fadd2(make_float2(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1])), make_float2(wb.z, wb.w));
+        for (int i = 0; i < 8; ++i) tb[i] = stab[(c >> 1) + i];
+        ptx::tmem_wait_ld16(acc);
+        if (c + 16 < 256) ptx::tmem_ld16_nowait(t_acc + c + 16, eacc[((c >> 4) + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 t = tb[i];
+          const float2 h = fadd2(make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])),
+                                 make_float2(__uint_as_float(t.w << 16), __uint_as_float(t.w & 0xffff0000u)));
           const float2 v = ffma2(h, make_float2(act_tanh<true>(h.x), act_tanh<true>(h.y)), h);   // SiLU(2h) = h + h tanh(h)
-          q0 = ffma2(v, make_float2(wa.x, wa.y), q0);
-          q1 = ffma2(v, make_float2(wa.z, wa.w), q1);
-          q2 = ffma2(v, make_float2(wb.x, wb.y), q2);
+          q0 = ffma2(v, make_float2(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u)), q0);
+          q1 = ffma2(v, make_float2(__uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u)), q1);
+          q2 = ffma2(v, make_float2(__uint_as_float(t.z << 16), __uint_as_float(t.z & 0xffff0000u)), q2);
         }
       }
-      const float s0 = q0.x + q0.y, s1 = q1.x + q1.y, s2 = q2.x + q2.y;
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_free[s]), 0));     // this warp's 32 lanes are drained
       if (ok) {
+        const float s0 = q0.x + q0.y, s1 = q1.x + q1.y, s2 = q2.x + q2.y;
         const float a2 = (fl & 1) ? 1.f : 0.f, asp = (fl & 2) ? 1.f : 0.f;
         a.wdir[d_out] = (act_tanh<true>(s0) + act_tanh<true>(s1) * a2 + act_tanh<true>(s2) * asp) / 3.0f;
       }
-      ptx::tc_fence_before();
-      group_sync(g);
-      if (r == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_free[s]), 0));
     }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // warps 14, 15: their registers go to the build warps
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();           // the peer may still be read by / written from the leader's MMAs until here
-  if (warp == 9) {
+  if (warp == 13) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_2sm<512>(tmem_base);
   }
+}
+
+// Modulate vectors of the coordinate heads of ALL blocks as bf16, once per denoiser call: cmod[(l * B + b) * 512 + c] =
+// shift[c] (c < 256) | 1 + scale[c - 256], from the fp32 adaLN table (ADA_COORD columns of block l).
+__global__ void __launch_bounds__(256) k_coord_mod(int B, const float* __restrict__ ada, bf16* __restrict__ cmod) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
+  const float* ar = ada + static_cast<size_t>(b) * ADA_LD + l * ADA_BLK + ADA_COORD;
+  bf16* o = cmod + (static_cast<size_t>(l) * B + b) * 512;
+  o[t] = __float2bfloat16_rn(ar[t]);
+  o[256 + t] = __float2bfloat16_rn(1.0f + ar[256 + t]);
 }
 
 // ----------------------------------------------------------------------------- probe: one cta_group::2 MMA tile
@@ -432,7 +502,7 @@ umma2_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 }  // namespace
 
-int coord_head_launch(DsContext* ctx, const Plan& plan, const void* X, const void* ab, const float* ada_l, const uint8_t* pflags,
+int coord_head_launch(DsContext* ctx, const Plan& plan, const void* X, const void* ab, const void* cmod_l, const uint8_t* pflags,
                       const void* we, const void* wc1, const float* bc1, const float* wc2, float* wdir, cudaStream_t s) {
   if (plan.Mp <= 0) return DS_OK;
   static bool attr_set[64] = {};            // the attribute is per device: one flag per device ordinal
@@ -447,20 +517,29 @@ int coord_head_launch(DsContext* ctx, const Plan& plan, const void* X, const voi
   DS_TRY(ds_make_tmap_2d(ctx, &tmAB, ab, plan.Mn, 512, 512, 64, kWinRows, false));
   CoordHeadArgs a;
   a.ab = reinterpret_cast<const bf16*>(ab);
-  a.ada = ada_l + ADA_COORD;
+  a.cmod = reinterpret_cast<const bf16*>(cmod_l);
+  a.bc1 = bc1;
+  a.wc2 = wc2;
   a.pflags = pflags;
   a.pair_info = plan.pair_info;
   a.pair_rows = plan.pair_rows;
   a.n_atoms = plan.n_atoms;
   a.poff = plan.poff;
-  a.bc1 = bc1;
-  a.wc2 = wc2;
   a.wdir = wdir;
   a.Mp = plan.Mp;
+  a.dbg = nullptr;
+  if (const char* e = getenv("DS_COORD_DBG")) a.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));   // developer aid: device pointer
   const int tiles = (plan.Mp + TM - 1) / TM;
   const int max_cl = ctx->num_sms / 2;
   const int ncl = tiles < max_cl ? tiles : max_cl;
   ds_launch(coord_head_kernel, dim3(2 * ncl), dim3(kThreads), kSmem, s, tmX, tmWe, tmWc1, tmAB, a);
+  DS_CUDA_CHECK(cudaGetLastError());
+  ctx->launch_count++;
+  return DS_OK;
+}
+
+int coord_mod_launch(DsContext* ctx, int B, int n_blocks, const float* ada, void* cmod, cudaStream_t s) {
+  ds_launch(k_coord_mod, dim3(B, n_blocks), dim3(256), 0, s, B, ada, reinterpret_cast<bf16*>(cmod));
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;
   return DS_OK;

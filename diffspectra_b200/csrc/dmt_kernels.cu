@@ -1197,6 +1197,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
                 ACT_SILU, s));
   DS_TRY(linear(ctx, w.s_act, D_TIME, pw.w_ada, D_TIME, pw.b_ada, nullptr, 0, w.ada, ADA_LD, DT_F32, B, ADA_LD, D_TIME,
                 ACT_NONE, s));
+  if (kFast && (ctx->fuse_mask & 16) && Mp > 0) DS_TRY(coord_mod_launch(ctx, B, N_LAYERS, w.ada, w.cmod, s));
   // root embeddings
   ds_launch(k_root_nodes<AT>, dim3(Mn), dim3(256), 0, s, Mn, xs, cond_x, pw.node_emb_w, pw.node_emb_b, w.h, reinterpret_cast<AT*>(w.hb),
                                       reinterpret_cast<AT*>(w.ahid), w.pos);
@@ -1361,7 +1362,8 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       // ---- equivariant coordinate update (needs both chains)
       if (kFast && (ctx->fuse_mask & 16)) {
         // whole coordinate head in one kernel on CTA pairs: G stays in TMEM, the LN+modulate operand in shared memory
-        DS_TRY(coord_head_launch(ctx, plan, X, w.ab, ada_l, w.pflags, bw.we, bw.wc1, bw.bc1, bw.wc2, w.wdir, s));
+        DS_TRY(coord_head_launch(ctx, plan, X, w.ab, reinterpret_cast<const bf16*>(w.cmod) + static_cast<size_t>(l) * B * 512, w.pflags, bw.we,
+                                 bw.wc1, bw.bc1, bw.wc2, w.wdir, s));
       } else {
         if (kFast && (ctx->fuse_mask & 32))
           ds_launch(k_coord_ln_async, dim3(cdiv(Mn, 8)), dim3(256), 0, s, plan, reinterpret_cast<const bf16*>(w.ab),
@@ -1482,6 +1484,7 @@ size_t denoise_ws_carve(Arena& a, DenoiseWs& w, int B, int Mn, int Mp, bool bf, 
   w.u1 = a.take(md * 256 * es);
   w.wdir = static_cast<float*>(a.take(md * 4));
   w.flags = static_cast<int*>(a.take(16));
+  w.cmod = wo ? nullptr : a.take(static_cast<size_t>(N_LAYERS) * b * 512 * 2);
   w.pab = wo ? static_cast<float*>(a.take(mn * 128 * 4)) : nullptr;
   w.eb = wo ? a.take(mp * 64 * es) : nullptr;
   w.pred_dir = wo ? static_cast<float*>(a.take(mp * 2 * 4)) : nullptr;

@@ -136,6 +136,7 @@ struct DenoiseWs {      // scratch of one denoiser call on a plan (sizes in elem
   void* Z;              // act [2Mp,256]
   void* u1;             // act [2Mp,256]
   float* wdir;          // [2Mp]
+  void* cmod;           // bf16 [8][B][512] modulate vectors of the coordinate heads (shift | 1 + scale), fused coordinate head
   int* flags;           // [4] 0: any cond distance non-zero, 1: NaN seen
   // DMT_WO_EQ only (edge buffers above are then sized per DIRECTED edge)
   float* pab;           // [Mn,128] node2edge_lin halves applied per atom: [W[:, :256] hn | W[:, 256:] hn]
@@ -165,8 +166,10 @@ int denoise_wo_eq_packed(DsContext* ctx, const PackedWeights& pw, const Plan& pl
 
 // fused coordinate head of one block (coord_head_tc.cu): pair part of input_lin -> LayerNorm + modulate -> coord_mlp ->
 // w[d], on CTA pairs (cta_group::2 MMAs); X = the [dist | e] operand [Mp,128] bf16, ab = hoisted per-atom parts [Mn,512] bf16
-int coord_head_launch(DsContext* ctx, const Plan& plan, const void* X, const void* ab, const float* ada_l, const uint8_t* pflags,
+// cmod_l = this block's [B][512] bf16 modulate vectors (shift | 1 + scale), written once per call by coord_mod_launch
+int coord_head_launch(DsContext* ctx, const Plan& plan, const void* X, const void* ab, const void* cmod_l, const uint8_t* pflags,
                       const void* we, const void* wc1, const float* bc1, const float* wc2, float* wdir, cudaStream_t s);
+int coord_mod_launch(DsContext* ctx, int B, int n_blocks, const float* ada, void* cmod, cudaStream_t s);   // cmod [n_blocks][B][512] bf16
 // one cta_group::2 MMA tile: out[256,256] f32 = A[256,K] W[256,K]^T (test probe of the CTA-pair operand split)
 int umma2_probe_launch(DsContext* ctx, const void* A, const void* W, float* out, int K, cudaStream_t s);
 

@@ -164,10 +164,11 @@ int ds_umma2_probe(ds_ctx* ctx, const void* A, const void* W, float* out, int K,
  * d = (r -> c) of the plan, wdir[d] = mean(tanh(wc2 . SiLU(2 (wc1_half . z + bc1_half))) * [1, adj2d, adjsp]) with
  * z = modulate(LayerNorm(ab[r][0:256] + ab[c][256:512] + we . X[pair]), ada[mol][1920:2176], ada[mol][2176:2432]).
  * X[Mp,128], ab[Mn,512], we[256,128], wc1_half[256,256] bf16; ada_block = adaLN table of the block (row stride 19584 floats);
- * pflags[Mp] adjacency bits; wdir[2 Mp] source-major (d = 2 poff[mol] + r (n-1) + c - (c > r)). */
+ * pflags[Mp] adjacency bits; wdir[2 Mp] source-major (d = 2 poff[mol] + r (n-1) + c - (c > r)); scratch = B * 1024 bytes
+ * (bf16 copy of the modulate vectors). */
 int ds_coord_head(ds_ctx* ctx, const void* plan, int B, int N, int Mn, int Mp, const void* X, const void* ab,
                   const float* ada_block, const unsigned char* pflags, const void* we, const void* wc1_half,
-                  const float* bc1_half, const float* wc2, float* wdir, void* stream);
+                  const float* bc1_half, const float* wc2, float* wdir, void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

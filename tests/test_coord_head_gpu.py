@@ -63,7 +63,7 @@ def test_coord_head_matches_torch(ctx, case):
         n = np.array([18], dtype=np.int32)
     elif case == 'small':
         n = np.array([29, 1, 4, 17, 2, 23, 9, 1, 1, 12, 3, 29], dtype=np.int32)
-    elif case == 'tiny_molecules':           # many molecules per 128-pair tile: atoms beyond the 56-atom window
+    elif case == 'tiny_molecules':           # many molecules per 128-pair tile: atoms beyond the 48-atom window
         n = np.tile(np.array([3, 2, 4, 1, 5], dtype=np.int32), 60)
     elif case == 'configs1':
         n = W.sample_n_atoms(1024, seed=1234).numpy().astype(np.int32)
@@ -89,8 +89,9 @@ def test_coord_head_matches_torch(ctx, case):
     ada[:, ADA_COORD:ADA_COORD + 512] = torch.randn(B, 512, device='cuda', generator=g) * 0.3
     pflags = torch.randint(0, 4, (max(Mp, 1),), device='cuda', generator=g, dtype=torch.uint8)
     wdir = torch.full((2 * Mp + 8,), -7.0, device='cuda')
+    scratch = torch.empty(B * 1024, dtype=torch.uint8, device='cuda')
     L.check(L.lib().ds_coord_head(ctx, *plan.args(), L.ptr(X), L.ptr(ab), L.ptr(ada), L.ptr(pflags), L.ptr(we), L.ptr(wc1h),
-                                  L.ptr(bc1h), L.ptr(wc2), L.ptr(wdir), L.stream_ptr()), 'ds_coord_head')
+                                  L.ptr(bc1h), L.ptr(wc2), L.ptr(wdir), L.ptr(scratch), L.stream_ptr()), 'ds_coord_head')
     torch.cuda.synchronize()
     # torch restatement (fp32 on the same bf16 operands; the kernel rounds z to bf16 before coord_mlp.0)
     G = X.float() @ we.float().t()
@@ -107,5 +108,7 @@ def test_coord_head_matches_torch(ctx, case):
     err = (wdir[:2 * Mp] - ref[:2 * Mp]).abs()
     print(case, 'Mn %d Mp %d max err %.2e mean err %.2e' % (Mn, Mp, err.max().item() if Mp else 0, err.mean().item() if Mp else 0))
     assert torch.isfinite(wdir).all()
-    assert err.max().item() < 5e-3
+    # bf16 roundings inside the kernel the fp32 restatement does not have: A + B, y, LN(y), the modulate vectors, the
+    # coord_mlp.2 / bias table; |w| <= 1
+    assert err.max().item() < 1.5e-2 and err.mean().item() < 2e-3
     assert (wdir[2 * Mp:] == -7).all()
