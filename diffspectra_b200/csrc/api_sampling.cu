@@ -26,6 +26,12 @@ struct CtxFull : DsContext {
 
 inline CtxFull* full(ds_ctx* h) { return reinterpret_cast<CtxFull*>(h); }
 
+// Last kernel of the body of the WHILE node that holds one sampling step: the loop goes on while the device-side step
+// counter (incremented by the step itself) is below the end of the segment.  step[0] = current step, step[1] = end.
+__global__ void k_loop_condition(cudaGraphConditionalHandle handle, const int* __restrict__ step) {
+  if (threadIdx.x == 0) cudaGraphSetConditional(handle, step[0] < step[1] ? 1u : 0u);
+}
+
 // plan blob layout (device, int32): n_atoms[B] | noff[B+1] | poff[B+1] | node_info[Mn_max] | pair_info[Mp_max] |
 // dir_info[2*Mp_max] (int4) | dir_mol[2*Mp_max] | pair_rows[Mp_max] (int2) | mol_order[B] | node_order[Mn_max] | mol_launch[B] (int4) | atom_launch[Mn_max] (int4)
 struct PlanLayout {
@@ -321,7 +327,10 @@ int ds_sample_loop(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp
     DS_CUDA_CHECK(cudaMemsetAsync(lw.pred_x, 0, size_t(Mn) * 9 * 4, s));
     DS_CUDA_CHECK(cudaMemsetAsync(lw.pred_e, 0, size_t(Mp > 0 ? Mp : 1) * 2 * 4, s));
   }   // else: continue from the state a previous segment left in the workspace
-  DS_CUDA_CHECK(cudaMemcpyAsync(lw.step, &first_step, 4, cudaMemcpyHostToDevice, s));
+  // device-side loop state: step[0] = current step, step[1] = end of this segment.  Pageable host memory: the copy is
+  // staged by the runtime before cudaMemcpyAsync returns, so the stack array may die at return.
+  const int loop_state[2] = {first_step, first_step + steps};
+  DS_CUDA_CHECK(cudaMemcpyAsync(lw.step, loop_state, sizeof(loop_state), cudaMemcpyHostToDevice, s));
   StepRef sr{coef_table, lw.step};
 
   auto one_step = [&]() -> int {
@@ -334,14 +343,17 @@ int ds_sample_loop(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp
   if (!use_graph) {
     for (int i = 0; i < steps; ++i) DS_TRY(one_step());
   } else {
-    // One step is captured once (all kernels read the step index from device memory) and replayed `steps` times.
+    // The whole loop is ONE graph launch: a WHILE conditional node whose body is one captured step (all kernels read the
+    // step index from device memory; the body's last kernel re-arms the condition while step < end).  DS_LOOP_GRAPH=0
+    // falls back to replaying a one-step graph `steps` times from the host.
     GraphKey key;
     memset(&key, 0, sizeof(key));
     key.ws = workspace; key.plan = plan_dev; key.ctx_emb = ctx_emb; key.coef = coef_table;
     key.raw_pos = raw_pos; key.raw_h = raw_h; key.raw_e = raw_e; key.pw_blob = c->pw.w_ada;
     key.B = B; key.N = N; key.Mn = Mn; key.Mp = Mp; key.seed = seed; key.gid_base = gid_base; key.temperature = temperature;
     key.first_step = raw_pos ? first_step : 0;
-    if (c->step_graph == nullptr || memcmp(&c->gkey, &key, sizeof(key)) != 0) {
+    const bool whole_loop = c->loop_graph != 0;
+    if (c->step_graph == nullptr || memcmp(&c->gkey, &key, sizeof(key)) != 0 || c->step_graph_is_loop != whole_loop) {
       if (c->step_graph) {
         cudaGraphExecDestroy(c->step_graph);
         c->step_graph = nullptr;
@@ -352,25 +364,57 @@ int ds_sample_loop(ds_ctx* h, const void* plan_dev, int B, int N, int Mn, int Mp
       if (c->capture_stream == nullptr) DS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
       cudaStream_t user_stream = s;
       s = c->capture_stream;
-      DS_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      int r = one_step();
-      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      int r = DS_OK;
+      cudaError_t ce = cudaSuccess;
+      if (whole_loop) {
+        DS_CUDA_CHECK(cudaGraphCreate(&graph, 0));
+        cudaGraphConditionalHandle handle;
+        DS_CUDA_CHECK(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        DS_CUDA_CHECK(cudaGraphAddNode(&node, graph, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        DS_CUDA_CHECK(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        r = one_step();
+        if (r == DS_OK) {
+          k_loop_condition<<<1, 32, 0, s>>>(handle, lw.step);
+          c->launch_count++;
+        }
+        ce = cudaStreamEndCapture(s, nullptr);
+      } else {
+        DS_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        r = one_step();
+        ce = cudaStreamEndCapture(s, &graph);
+      }
       s = user_stream;
       if (r != DS_OK) {
         if (graph) cudaGraphDestroy(graph);
         return r;
       }
-      DS_CUDA_CHECK(ce);
+      if (ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        DS_CUDA_CHECK(ce);
+      }
       c->step_graph_launches = c->launch_count - before;
       c->launch_count = before;
       cudaError_t ie = cudaGraphInstantiate(&c->step_graph, graph, 0);
       cudaGraphDestroy(graph);
       DS_CUDA_CHECK(ie);
       c->gkey = key;
+      c->step_graph_is_loop = whole_loop;
     }
-    for (int i = 0; i < steps; ++i) {
+    if (whole_loop) {
       DS_CUDA_CHECK(cudaGraphLaunch(c->step_graph, s));
-      c->launch_count += c->step_graph_launches;
+      c->launch_count += c->step_graph_launches * steps;
+    } else {
+      for (int i = 0; i < steps; ++i) {
+        DS_CUDA_CHECK(cudaGraphLaunch(c->step_graph, s));
+        c->launch_count += c->step_graph_launches;
+      }
     }
   }
   // the reference returns the MEANS of the last step (sampling.py:628-629)

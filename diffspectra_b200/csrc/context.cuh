@@ -15,7 +15,7 @@ struct DsContext {
   int model_kind = 0;        // 0 = DMT (models/dmt.py), 1 = DMT_WO_EQ ablation (models/dmt_wo_eq.py)
   int num_sms = 148;
   void* encode_tiled = nullptr;      // cuTensorMapEncodeTiled (driver entry point, resolved at run time)
-  int fuse_mask = 239;                // debug: bit0 LNMOD, bit1 RESGATE(node), bit2 RESGATE(edge), bit3 COORD epilogue, bit4 fused coordinate head on CTA pairs (coord_head_tc.cu: replaces the gp GEMM, k_coord_ln and the COORD GEMM), bit5 cp.async-prefetching k_coord_ln, bit6 fused edge FFN (edge_ffn_tc.cu: 62 us vs 86 us for the three kernels it replaces), bit7 coordinate update of block l-1 fused into the RBF kernel of block l (k_pos_rbf, per-molecule CTAs; both precision modes)
+  int fuse_mask = 255;                // debug: bit0 LNMOD, bit1 RESGATE(node), bit2 RESGATE(edge), bit3 COORD epilogue, bit4 fused coordinate head on CTA pairs (coord_head_tc.cu: replaces the gp GEMM, k_coord_ln and the COORD GEMM), bit5 cp.async-prefetching k_coord_ln, bit6 fused edge FFN (edge_ffn_tc.cu: 62 us vs 86 us for the three kernels it replaces), bit7 coordinate update of block l-1 fused into the RBF kernel of block l (k_pos_rbf, per-molecule CTAs; both precision modes)
   // node-chain / edge-chain overlap inside a block (dmt_kernels.cu): the atom-side kernels (18 k rows, one tile per
   // SM, latency-bound) run on a side stream next to the pair-side kernels; persistent GEMM grids are capped so that
   // both fit on the 148 SMs at once.  Opt-in experiment: DS_OVERLAP=1 enables, DS_SPLIT=edge,node sets the caps.
@@ -32,6 +32,10 @@ struct DsContext {
   cudaGraphExec_t step_graph = nullptr;
   cudaStream_t capture_stream = nullptr;
   long long step_graph_launches = 0;   // kernels inside one replay of step_graph
+  bool step_graph_is_loop = false;     // step_graph holds the WHILE node (whole loop in one launch) rather than one step
+  int loop_graph = 0;                  // DS_LOOP_GRAPH: 1 = the whole sampling loop is ONE graph launch (WHILE conditional node whose body is a step);
+                                       // measured on B200 at 200 steps: 754.6 ms per round vs 742.5 ms for 200 host launches of the one-step graph
+                                       // (+60 us per iteration of the conditional node), hence off by default
 };
 
 inline bool ds_is_bf16(const DsContext* c) { return c->mode == 1; }

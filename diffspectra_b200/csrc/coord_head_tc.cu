@@ -40,18 +40,19 @@ namespace {
 
 constexpr int TM = 128;                  // pairs per tile = rows per CTA of the M = 256 MMAs
 constexpr int kKb = 16 * 1024;           // one k-block tile: 128 rows x 64 bf16, SWIZZLE_128B
-constexpr int kWinRows = 56;             // atoms in the window
-constexpr int kWinBox = kWinRows * 128;  // 7168 B: 56 rows x 64 bf16
+constexpr int kWinRows = 48;             // atoms in the window
+constexpr int kWinBox = kWinRows * 128;  // 6144 B: 48 rows x 64 bf16
 constexpr int OFF_WC1 = 0;               // coord_mlp.0 rows [128 rank, +128): 4 k-blocks
 constexpr int OFF_WE = 4 * kKb;          // input_lin[e | dist] rows [128 rank, +128): 2 k-blocks
 constexpr int OFF_Z = 6 * kKb;           // operand tile of MMA2: 4 k-blocks
 constexpr int OFF_X = 10 * kKb;          // operand tile of MMA1: 2 k-blocks
-constexpr int OFF_WIN = 12 * kKb;        // 4 boxes of 56 atoms x 64 channels
-constexpr int OFF_TAB = OFF_WIN + 4 * kWinBox;   // [128] uint4, one per column pair: bf16x2 of coord_mlp.2 rows 0, 1, 2 and of the coord_mlp.0 bias
-constexpr int OFF_STAT = OFF_TAB + 2048;         // [2][128] float2 LayerNorm partials of the two channel halves
-constexpr int OFF_BAR = OFF_STAT + 2048;
+constexpr int OFF_WIN = 12 * kKb;        // 4 boxes of 48 atoms x 64 channels
+constexpr int OFF_TAB = OFF_WIN + 4 * kWinBox;   // [256] float4: per column PAIR (2p, 2p+1): [2p] = (w0, w0', w1, w1'), [2p+1] = (w2, w2', bias, bias')
+constexpr int OFF_STAT = OFF_TAB + 4096;         // [2][128] float2 LayerNorm partials of the two channel halves
+constexpr int OFF_PART = OFF_STAT + 2048;        // [128] float4 epilogue partial sums of the upper channel half
+constexpr int OFF_BAR = OFF_PART + 2048;
 constexpr int kSmem = OFF_BAR + 256;
-constexpr int kThreads = 512;             // 8 build warps, 4 epilogue warps, loader, MMA issuer, 2 idle (register donors)
+constexpr int kThreads = 640;             // 8 build warps, 8 epilogue warps, loader, MMA issuer, 2 idle (register donors)
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 struct CoordHeadArgs {
@@ -76,7 +77,8 @@ struct CoordHeadArgs {
 __device__ __forceinline__ void wait_guard(uint64_t* bar, uint32_t parity, int tag, int it) {
   uint32_t spins = 0;
   while (!ptx::mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
+    __nanosleep(40);            // a spinning warp takes issue slots from the warps it is waiting for
+    if (++spins > (1u << 22)) {
       printf("coord_head_kernel: wait timeout tag=%d it=%d block=%d thread=%d parity=%u\n", tag, it, blockIdx.x, threadIdx.x, parity);
       __trap();
     }
@@ -126,7 +128,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int n_tiles = (a.Mp + TM - 1) / TM;
   const int my_n = (n_tiles - cid + ncl - 1) / ncl;
 
-  if (warp == 12 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     if (ptx::smem_u32(smem) & 1023u) __trap();
     ptx::prefetch_tmap(&tmX);
     ptx::prefetch_tmap(&tmWe);
@@ -139,18 +141,18 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&g_full[i], 1);
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&tmem_free[i], 8);       // one arrival per epilogue warp of both CTAs
+      ptx::mbar_init(&tmem_free[i], 16);      // one arrival per epilogue warp of both CTAs
     }
     ptx::mbar_init(win_full, 1);
     ptx::mbar_init(win_free, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 13) ptx::tmem_alloc_2sm<512>(tmem_slot);
-  if (threadIdx.x < 128) {       // epilogue table: the load/store return path (128 B/clk) is this kernel's scarcest resource and the
-    const int c = 2 * threadIdx.x;   // table is read once per (row, column): bf16 pairs halve those bytes
-    reinterpret_cast<uint4*>(smem + OFF_TAB)[threadIdx.x] =
-        make_uint4(pack2(a.wc2[c], a.wc2[c + 1]), pack2(a.wc2[256 + c], a.wc2[257 + c]), pack2(a.wc2[512 + c], a.wc2[513 + c]),
-                   pack2(a.bc1[c], a.bc1[c + 1]));
+  if (warp == 17) ptx::tmem_alloc_2sm<512>(tmem_slot);
+  if (threadIdx.x < 256) {     // epilogue table (fp32: unpacking a bf16 table costs more issue slots than the smaller loads save)
+    const int c2 = threadIdx.x & ~1;
+    reinterpret_cast<float4*>(smem + OFF_TAB)[threadIdx.x] =
+        (threadIdx.x & 1) ? make_float4(a.wc2[512 + c2], a.wc2[513 + c2], a.bc1[c2], a.bc1[c2 + 1])
+                          : make_float4(a.wc2[c2], a.wc2[c2 + 1], a.wc2[256 + c2], a.wc2[257 + c2]);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -159,7 +161,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  if (warp == 12) {
+  if (warp == 16) {
     // ===================== loader =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
@@ -181,7 +183,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int b = 0; b < 4; ++b) ptx::tma_load_2d(smem + OFF_WIN + b * kWinBox, &tmAB, win_full, (rank ? 0 : 256) + 64 * b, a_lo);
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == 17) {
     // ===================== MMA issuer (leader CTA, one thread, for both CTAs) =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (rank == 0 && lane == 0) {
@@ -239,7 +241,8 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     //   pass B(t)   normalise + modulate from the registers -> operand tile Z -> MMA2(t)
     // and straight on to tile t+1 while the epilogue warps drain tile t: the build is bound by TMEM reads, the load/store
     // return path and issue slots, the epilogue by MUFU.TANH, so the two overlap on one SM.
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    // register pool of the CTA = 640 threads x 96: 256 x 144 (build) + 256 x 72 (epilogue) + 128 x 40 (loader, MMA, idle) = 60 416 <= 61 440
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
     const int hf = warp >> 2, wq = warp & 3, r = wq * 32 + lane;     // r = row inside the tile = TMEM lane; hf = channel half
     const int cb = hf * 128;
     const uint32_t z_full_leader = ptx::mapa(ptx::smem_u32(z_full), 0);
@@ -328,10 +331,10 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (it >= 1) wait_guard(&acc_full[s ^ 1], ((it - 1) >> 1) & 1, 7, it);
       DS_STAMP(4);
       // ---- pass B: normalise + modulate from the registers -> bf16 -> SWIZZLE_128B K-major operand row
-      const float nm = -mean * is;
-      const float2 is2 = make_float2(is, is), nm2 = make_float2(nm, nm);
-      // z = LN(y) (1 + scale) + shift with the modulate vectors as bf16 pairs (half the load bytes of the fp32 table) and the
-      // modulate itself as ONE packed bf16 fma per channel pair (fp32 inside, rounded once)
+      // z = (y rstd - mean rstd) (1 + scale) + shift as TWO packed bf16 fmas per channel pair (fp32 inside each, one rounding
+      // each): y is bf16 already, the modulate vectors arrive as bf16 pairs, so nothing is unpacked or re-packed.  The
+      // per-row factors rstd and -mean rstd are rounded to bf16 (a 2^-9 relative error of the row's scale).
+      const __nv_bfloat162 is2 = __float2bfloat162_rn(is), nm2 = __float2bfloat162_rn(-mean * is);
 #pragma unroll
       for (int hb = 0; hb < 2; ++hb) {
         uint4 shq[8], scq[8];
@@ -348,8 +351,8 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t w = yreg[hb * 32 + q * 4 + k];
-            const float2 n2 = ffma2(make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)), is2, nm2);
-            const __nv_bfloat162 z2 = __hfma2(__floats2bfloat162_rn(n2.x, n2.y), sc2[k], sh2[k]);
+            const __nv_bfloat162 n2 = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&w), is2, nm2);
+            const __nv_bfloat162 z2 = __hfma2(n2, sc2[k], sh2[k]);
             o[k] = *reinterpret_cast<const uint32_t*>(&z2);
           }
           *reinterpret_cast<uint4*>(zbuf + (2 * hf + hb) * kKb + r * 128 + ((q ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -360,12 +363,16 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (threadIdx.x == 0) ptx::mbar_arrive_cluster(z_full_leader);
       DS_STAMP(5);
     }
-  } else if (warp < 12) {
-    // ===================== epilogue warps: ONE thread per directed edge, all 256 columns =====================
-    //   u = SiLU(2 (acc + b/2)) ; s_o = wc2[o] . u ; w = mean(tanh(s) * [1, adj2d, adjsp])          (MUFU.TANH-bound)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    const int wq = warp & 3, r = wq * 32 + lane;
-    const uint4* stab = reinterpret_cast<const uint4*>(smem + OFF_TAB);
+  } else if (warp < 16) {
+    // ===================== epilogue warps: TWO threads per directed edge, 128 columns each =====================
+    //   u = SiLU(2 (acc + b/2)) ; s_o = wc2[o] . u ; w = mean(tanh(s) * [1, adj2d, adjsp])
+    // MUFU.TANH-bound (one tanh per accumulator element, measured ~8 per clock per SM): two warps per scheduler keep the
+    // special-function unit fed while the build warps use the other pipes.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int hf = (warp - 8) >> 2, wq = warp & 3, r = wq * 32 + lane;
+    const int cb = hf * 128;
+    const float4* stab = reinterpret_cast<const float4*>(smem + OFF_TAB) + cb;
+    float4* spart = reinterpret_cast<float4*>(smem + OFF_PART);      // [128] partial sums of the upper channel half
     for (int it = 0; it < my_n; ++it) {
       const int s = it & 1;
       const int p0 = (cid + it * ncl) * TM;
@@ -377,48 +384,55 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int nat = __ldg(a.n_atoms + mol), pb = __ldg(a.poff + mol);
       const uint8_t fl = __ldg(a.pflags + pc);
       const size_t d_out = static_cast<size_t>(2) * pb + (rank ? static_cast<size_t>(aj) * (nat - 1) + ai : static_cast<size_t>(ai) * (nat - 1) + (aj - 1));
-      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(s * 256);
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(s * 256 + cb);
       wait_guard(&acc_full[s], (it >> 1) & 1, 8, it);
       ptx::tc_fence_after();
-      float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0;
+      float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0, q4 = q0, q5 = q0;     // two chains per output
       uint32_t eacc[2][16];
       ptx::tmem_ld16_nowait(t_acc, eacc[0]);
 #pragma unroll 2
-      for (int c = 0; c < 256; c += 16) {
+      for (int c = 0; c < 128; c += 16) {
         uint32_t (&acc)[16] = eacc[(c >> 4) & 1];
-        uint4 tb[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tb[i] = stab[(c >> 1) + i];
         ptx::tmem_wait_ld16(acc);
-        if (c + 16 < 256) ptx::tmem_ld16_nowait(t_acc + c + 16, eacc[((c >> 4) + 1) & 1]);
+        if (c + 16 < 128) ptx::tmem_ld16_nowait(t_acc + c + 16, eacc[((c >> 4) + 1) & 1]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 t = tb[i];
-          const float2 h = fadd2(make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])),
-                                 make_float2(__uint_as_float(t.w << 16), __uint_as_float(t.w & 0xffff0000u)));
+        for (int i = 0; i < 16; i += 2) {
+          const float4 wa = stab[c + i], wb = stab[c + i + 1];
+          const float2 h = fadd2(make_float2(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1])), make_float2(wb.z, wb.w));
           const float2 v = ffma2(h, make_float2(act_tanh<true>(h.x), act_tanh<true>(h.y)), h);   // SiLU(2h) = h + h tanh(h)
-          q0 = ffma2(v, make_float2(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u)), q0);
-          q1 = ffma2(v, make_float2(__uint_as_float(t.y << 16), __uint_as_float(t.y & 0xffff0000u)), q1);
-          q2 = ffma2(v, make_float2(__uint_as_float(t.z << 16), __uint_as_float(t.z & 0xffff0000u)), q2);
+          if (i & 2) {
+            q3 = ffma2(v, make_float2(wa.x, wa.y), q3);
+            q4 = ffma2(v, make_float2(wa.z, wa.w), q4);
+            q5 = ffma2(v, make_float2(wb.x, wb.y), q5);
+          } else {
+            q0 = ffma2(v, make_float2(wa.x, wa.y), q0);
+            q1 = ffma2(v, make_float2(wa.z, wa.w), q1);
+            q2 = ffma2(v, make_float2(wb.x, wb.y), q2);
+          }
         }
       }
+      float s0 = (q0.x + q0.y) + (q3.x + q3.y), s1 = (q1.x + q1.y) + (q4.x + q4.y), s2 = (q2.x + q2.y) + (q5.x + q5.y);
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_free[s]), 0));     // this warp's 32 lanes are drained
-      if (ok) {
-        const float s0 = q0.x + q0.y, s1 = q1.x + q1.y, s2 = q2.x + q2.y;
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_free[s]), 0));     // this warp's columns are drained
+      if (hf == 1) spart[r] = make_float4(s0, s1, s2, 0.f);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (hf == 0 && ok) {
+        const float4 o = spart[r];
+        s0 += o.x; s1 += o.y; s2 += o.z;
         const float a2 = (fl & 1) ? 1.f : 0.f, asp = (fl & 2) ? 1.f : 0.f;
         a.wdir[d_out] = (act_tanh<true>(s0) + act_tanh<true>(s1) * a2 + act_tanh<true>(s2) * asp) / 3.0f;
       }
+      asm volatile("bar.sync 2, 256;" ::: "memory");          // spart may be overwritten by the next tile
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // warps 14, 15: their registers go to the build warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // warps 18, 19: their registers go to the build warps
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();           // the peer may still be read by / written from the leader's MMAs until here
-  if (warp == 13) {
+  if (warp == 17) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_2sm<512>(tmem_base);
   }
