@@ -437,7 +437,7 @@ def run_ours(args):
 
 def _demangle(name):
     import re
-    m = re.search(r'\d+(k_[a-z0-9_]+|gemm_tc_kernel|gemm_simt_kernel|coord_fused_kernel|edge_ffn_kernel)', name)
+    m = re.search(r'\d+(k_[a-z0-9_]+|gemm_tc_kernel|gemm_simt_kernel|coord_head_kernel|edge_ffn_kernel)', name)
     base = m.group(1) if m else name[:40]
     t = re.search(r'gemm_tc_kernelILi(\d+)ELi(\d+)ELb(\d)E', name)
     if t:
@@ -495,6 +495,7 @@ def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args, w):
         'k_attention_grp': Mp * 1024 + Mp + Mn * (1536 + 256 * 6),          # e0|e1 once per pair, flags, q|k|v, hn fp32+bf16
         'k_wo_attention': Md * 1024 + Mn * (1536 + 512),
         'k_coord_ln': Mp * 512 + Mn * 1024 + Md * 513,                       # gp, ab in; Z + flags out
+        'coord_head_kernel': Mp * (256 + 1) + Mn * 1024 + Md * 4,            # X in, pair flags, per-atom table ab (L2-resident), w out
         'edge_ffn_kernel': Mp * (256 + 256 + 128) + Mn * 256,               # e in, e out, bf16 copy out, hoisted node2edge rows
         'k_edge_update1': Mp * (256 + 256 + 128) + Mn * 256,
         'k_wo_edge_update1': Md * (256 + 256 + 128) + Mn * 512,
@@ -523,6 +524,8 @@ def step_kernel_profile(eng, plan, coef, spectra_dev, n_atoms, args, w):
             for key, v in bytes_of.items():
                 if kname.startswith(key):
                     by = v
+            if kname.startswith('coord_head_kernel'):      # pair part of input_lin once per pair + coord_mlp.0 per directed edge
+                flops = 2.0 * Mp * 128 * 256 + 2.0 * Md * 256 * 256
         t = us / n * 1e-6
         if flops:
             rec['tflops'] = flops / t / 1e12

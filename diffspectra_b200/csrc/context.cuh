@@ -15,7 +15,7 @@ struct DsContext {
   int model_kind = 0;        // 0 = DMT (models/dmt.py), 1 = DMT_WO_EQ ablation (models/dmt_wo_eq.py)
   int num_sms = 148;
   void* encode_tiled = nullptr;      // cuTensorMapEncodeTiled (driver entry point, resolved at run time)
-  int fuse_mask = 255;                // debug: bit0 LNMOD, bit1 RESGATE(node), bit2 RESGATE(edge), bit3 COORD epilogue, bit4 fused coordinate head on CTA pairs (coord_head_tc.cu: replaces the gp GEMM, k_coord_ln and the COORD GEMM), bit5 cp.async-prefetching k_coord_ln, bit6 fused edge FFN (edge_ffn_tc.cu: 62 us vs 86 us for the three kernels it replaces), bit7 coordinate update of block l-1 fused into the RBF kernel of block l (k_pos_rbf, per-molecule CTAs; both precision modes)
+  int fuse_mask = 511;                // debug: bit0 LNMOD, bit1 RESGATE(node), bit2 RESGATE(edge), bit3 COORD epilogue, bit4 fused coordinate head on CTA pairs (coord_head_tc.cu: replaces the gp GEMM, k_coord_ln and the COORD GEMM), bit5 cp.async-prefetching k_coord_ln, bit6 fused edge FFN (edge_ffn_tc.cu: 62 us vs 86 us for the three kernels it replaces), bit7 coordinate update of block l-1 fused into the RBF kernel of block l (k_pos_rbf, per-molecule CTAs; both precision modes), bit8 skip projection edge_l into the edge heads as a third MMA of edge_ffn_kernel (needs bit6)
   // node-chain / edge-chain overlap inside a block (dmt_kernels.cu): the atom-side kernels (18 k rows, one tile per
   // SM, latency-bound) run on a side stream next to the pair-side kernels; persistent GEMM grids are capped so that
   // both fit on the 148 SMs at once.  Opt-in experiment: DS_OVERLAP=1 enables, DS_SPLIT=edge,node sets the caps.

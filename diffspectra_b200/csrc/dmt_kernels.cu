@@ -1330,9 +1330,14 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
     if (Mp > 0) {
       // ---- pair chain B: residual + LN -> FFN -> residual; pair part of input_lin; skip projection
       ctx->cta_cap = ecap;
+      bool skip_done = false;
       if (kFast && (ctx->fuse_mask & 64)) {
         // the whole edge stream of the block in one kernel: e1 / f3 never leave the SM
-        DS_TRY(edge_ffn_launch(ctx, plan, w.e, X + 64, 128, w.pn, bw.n2e_b, ada_l, bw.ff3_w, bw.ff3_b, bw.ff4_w, bw.ff4_b, se));
+        // ... and the skip projection into the edge heads as a third MMA on the staged rows (DS_FUSE_MASK bit 8)
+        const bool fs = (ctx->fuse_mask & 256) != 0;
+        skip_done = fs;
+        DS_TRY(edge_ffn_launch(ctx, plan, w.e, X + 64, 128, w.pn, bw.n2e_b, ada_l, bw.ff3_w, bw.ff3_b, bw.ff4_w, bw.ff4_b,
+                               fs ? bw.edge_w : nullptr, bw.edge_b, reinterpret_cast<AT*>(w.ehid) + 64 + 16 * l, 192, se));
       } else {
       ds_launch(k_edge_update1<AT, kFast>, dim3(cdiv(Mp, 16)), dim3(256), 0, se, plan, w.e, w.pn, bw.n2e_b, w.ada, l, w.e1f,
                                                             reinterpret_cast<AT*>(w.e1b));
@@ -1354,8 +1359,9 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       if (!(kFast && (ctx->fuse_mask & 16)))       // the fused coordinate head computes the pair part of input_lin itself
         DS_TRY(linear(ctx, X, 128, bw.we, 128, nullptr, nullptr, 0, w.gp, 256, AD, Mp, 256, 128, ACT_NONE, se));
       // skip connection into the edge heads (dmt.py:387-388)
-      DS_TRY(linear(ctx, X + 64, 128, bw.edge_w, 64, bw.edge_b, nullptr, 0, reinterpret_cast<AT*>(w.ehid) + 64 + 16 * l,
-                    192, AD, Mp, 16, 64, ACT_NONE, se));
+      if (!skip_done)
+        DS_TRY(linear(ctx, X + 64, 128, bw.edge_w, 64, bw.edge_b, nullptr, 0, reinterpret_cast<AT*>(w.ehid) + 64 + 16 * l,
+                      192, AD, Mp, 16, 64, ACT_NONE, se));
     }
     DS_TRY(join());
     if (Mp > 0) {

@@ -13,7 +13,10 @@
 //   tcgen05.ld, SiLU, bf16 row into the second operand tile (same shared memory) -> MMA2 (accumulator re-uses the
 //   TMEM columns of MMA1) -> tcgen05.ld, gated residual on the registers kept since step one -> staged, coalesced
 //   stores of the fp32 stream and of its bf16 copy.
-// Three tiles are in flight per SM and the only cross-warp hand-offs are the four mbarriers per group shared with the
+// The bf16 copy of the updated row, staged in SWIZZLE_128B K-major form for its coalesced store, doubles as the operand of a
+// THIRD MMA: the block's skip projection into the edge heads, edge_l(e) [64 -> 16] (models/dmt.py:387-388), which used
+// to be a separate GEMM launch over all pairs.
+// Three tiles are in flight per SM and the only cross-warp hand-offs are the six mbarriers per group shared with the
 // single MMA-issuing thread (warp 12), which polls the groups round-robin.  Warp 13 loads the two 16 KB weight
 // matrices once.  32 KB of shared memory per group serve, in turn, as e staging, A1, A2 and output staging.
 #include "kernels.cuh"
@@ -27,8 +30,9 @@ constexpr int kThreads = (kGroups * 4 + 2) * 32;
 constexpr int kBuf = 32 * 1024;               // per group: e staging / A1 (first 16 KB) / A2 / output staging
 constexpr int kW3 = 128 * 64 * 2;             // ff_linear3 [128, 64] bf16
 constexpr int kW4 = 64 * 128 * 2;             // ff_linear4 [64, 128] bf16 as two k-blocks of [64 x 64]
-constexpr int kSmem = kGroups * kBuf + kW3 + kW4 + 1024 /*biases*/ + 256 /*barriers*/;
-constexpr uint32_t kGroupCols = 128;          // TMEM columns per group: acc1 [0,128), acc2 re-uses [0,64)
+constexpr int kWs = 16 * 64 * 2;              // edge_l [16, 64] bf16 (skip projection into the edge heads)
+constexpr int kSmem = kGroups * kBuf + kW3 + kW4 + kWs + 1024 /*biases*/ + 256 /*barriers*/;
+constexpr uint32_t kGroupCols = 128;          // TMEM columns per group: acc1 [0,128), acc2 re-uses [0,64), acc3 (skip) [64,80)
 
 struct EdgeFfnArgs {
   float* e;                  // [Mp,64] fp32 stream, updated in place
@@ -41,6 +45,9 @@ struct EdgeFfnArgs {
   const int2* pair_rows;     // atom rows of (i, j)
   const float* b3;           // [128] (halved together with W3: SiLU(x) = h + h tanh(h))
   const float* b4;           // [64]
+  const float* bs;           // [16] bias of the skip projection, or null: no skip output
+  bf16* skip;                // skip output: 16 columns per pair row, row stride lds (elements)
+  int lds;
   int Mp;
 };
 
@@ -61,13 +68,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // lanes reading 16 bytes each of 32 different P rows: 32 L1 wavefronts per load instruction, 32 such loads per thread).
 template <bool kCoop>
 __global__ void __launch_bounds__(kThreads, 1)
-edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmW4, EdgeFfnArgs a) {
+edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmW4,
+                const __grid_constant__ CUtensorMap tmWs, EdgeFfnArgs a) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smBuf = smem;                                   // [kGroups][32 KB]
   uint8_t* smW3 = smBuf + kGroups * kBuf;                  // 16 KB
   uint8_t* smW4 = smW3 + kW3;                              // 16 KB
-  float* sb3 = reinterpret_cast<float*>(smW4 + kW4);       // [128]
+  uint8_t* smWs = smW4 + kW4;                              // 2 KB
+  float* sb3 = reinterpret_cast<float*>(smWs + kWs);       // [128]
   float* sb4 = sb3 + 128;                                  // [64]
   float* sbn = sb4 + 64;                                   // [64] node2edge_lin bias
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb3 + 256);
@@ -75,8 +84,11 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
   uint64_t* t1_full = bars + kGroups;        // [3] MMA1 done
   uint64_t* a2_full = bars + 2 * kGroups;    // [3] group -> MMA: A2 written, acc1 drained
   uint64_t* t2_full = bars + 3 * kGroups;    // [3] MMA2 done
-  uint64_t* w_full = bars + 4 * kGroups;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kGroups + 1);
+  uint64_t* a3_full = bars + 4 * kGroups;    // [3] group -> MMA: bf16 row tile staged (operand of the skip projection)
+  uint64_t* t3_full = bars + 5 * kGroups;    // [3] MMA3 done
+  uint64_t* w_full = bars + 6 * kGroups;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 * kGroups + 1);
+  const bool has_skip = a.bs != nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (a.Mp + TM - 1) / TM;
@@ -86,11 +98,14 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
     if (ptx::smem_u32(smem) & 1023u) __trap();
     ptx::prefetch_tmap(&tmW3);
     ptx::prefetch_tmap(&tmW4);
+    ptx::prefetch_tmap(&tmWs);
     for (int i = 0; i < kGroups; ++i) {
       ptx::mbar_init(&a1_full[i], 128);
       ptx::mbar_init(&t1_full[i], 1);
       ptx::mbar_init(&a2_full[i], 128);
       ptx::mbar_init(&t2_full[i], 1);
+      ptx::mbar_init(&a3_full[i], 128);
+      ptx::mbar_init(&t3_full[i], 1);
     }
     ptx::mbar_init(w_full, 1);
     ptx::fence_barrier_init();
@@ -108,7 +123,8 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
   if (warp == 13) {
     // ===================== weights: L2 -> shared, once =====================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(w_full, kW3 + kW4);
+      ptx::mbar_arrive_expect_tx(w_full, kW3 + kW4 + (has_skip ? kWs : 0));
+      if (has_skip) ptx::tma_load_2d(smWs, &tmWs, w_full, 0, 0);      // [16 rows x 64 K]
       ptx::tma_load_2d(smW3, &tmW3, w_full, 0, 0);               // [128 rows x 64 K]
       ptx::tma_load_2d(smW4, &tmW4, w_full, 0, 0);               // k-block 0: [64 rows x K 0..63]
       ptx::tma_load_2d(smW4 + kW4 / 2, &tmW4, w_full, 64, 0);    // k-block 1
@@ -116,7 +132,7 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
   } else if (warp == 12) {
     // ===================== MMA issuer: serves the groups in whatever order their operands become ready =====================
     if (lane == 0) {
-      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(TM, 128), idesc2 = ptx::umma_idesc_bf16(TM, 64);
+      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(TM, 128), idesc2 = ptx::umma_idesc_bf16(TM, 64), idesc3 = ptx::umma_idesc_bf16(TM, 16);
       ptx::mbar_wait(w_full, 0);
       ptx::tc_fence_after();
       int left[kGroups], stage[kGroups];
@@ -142,6 +158,18 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
               ptx::umma_bf16(d, ptx::umma_smem_desc_sw128(buf + k * 32), ptx::umma_smem_desc_sw128(w_addr + k * 32), idesc1, k ? 1u : 0u);
             ptx::umma_commit(&t1_full[g]);
             stage[g] = 1;
+          } else if (stage[g] == 2) {
+            // skip projection: the staged bf16 rows [128 x 64] x edge_l^T [16 x 64] -> 16 accumulator columns
+            if (!ptx::mbar_try_wait(&a3_full[g], ph[g])) continue;
+            ptx::tc_fence_after();
+            const uint32_t w_addr = ptx::smem_u32(smWs);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16(d + 64, ptx::umma_smem_desc_sw128(buf + k * 32), ptx::umma_smem_desc_sw128(w_addr + k * 32), idesc3, k ? 1u : 0u);
+            ptx::umma_commit(&t3_full[g]);
+            stage[g] = 0;
+            ph[g] ^= 1;
+            if (--left[g] == 0) --open;
           } else {
             if (!ptx::mbar_try_wait(&a2_full[g], ph[g])) continue;
             ptx::tc_fence_after();
@@ -154,9 +182,13 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
                                (kb | k) ? 1u : 0u);
             }
             ptx::umma_commit(&t2_full[g]);
-            stage[g] = 0;
-            ph[g] ^= 1;
-            if (--left[g] == 0) --open;
+            if (has_skip) {
+              stage[g] = 2;
+            } else {
+              stage[g] = 0;
+              ph[g] ^= 1;
+              if (--left[g] == 0) --open;
+            }
           }
         }
       }
@@ -352,6 +384,10 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
         *reinterpret_cast<uint4*>(buf + r * 128 + ((c ^ (r & 7)) << 4)) =
             make_uint4(pack2(v[c * 8 + 0], v[c * 8 + 1]), pack2(v[c * 8 + 2], v[c * 8 + 3]), pack2(v[c * 8 + 4], v[c * 8 + 5]),
                        pack2(v[c * 8 + 6], v[c * 8 + 7]));
+      if (has_skip) {                              // the staged rows are also the operand of the skip projection
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&a3_full[g]);
+      }
       group_sync(g);
       {
         const int nrow = min(a.Mp - p0, TM);
@@ -361,6 +397,20 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
           if (row < nrow)
             *reinterpret_cast<uint4*>(a.xe + static_cast<size_t>(p0 + row) * a.ldx + ch * 8) =
                 *reinterpret_cast<const uint4*>(buf + row * 128 + ((ch ^ (row & 7)) << 4));
+        }
+      }
+      if (has_skip) {
+        ptx::mbar_wait(&t3_full[g], ph);           // MMA3 has also finished reading the staged rows
+        ptx::tc_fence_after();
+        uint32_t acc[16];
+        ptx::tmem_ld16_sync(t_addr + 64, acc);
+        if (ok) {
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = pack2(__uint_as_float(acc[2 * i]) + __ldg(a.bs + 2 * i), __uint_as_float(acc[2 * i + 1]) + __ldg(a.bs + 2 * i + 1));
+          uint4* dst = reinterpret_cast<uint4*>(a.skip + static_cast<size_t>(p) * a.lds);
+          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
       }
       group_sync(g);                               // staging reads done before the next tile overwrites the buffer
@@ -379,7 +429,8 @@ edge_ffn_kernel(const __grid_constant__ CUtensorMap tmW3, const __grid_constant_
 }  // namespace
 
 int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ldx, const float* pn, const float* n2e_b,
-                    const float* ada_l, const void* w3, const float* b3, const void* w4, const float* b4, cudaStream_t s) {
+                    const float* ada_l, const void* w3, const float* b3, const void* w4, const float* b4, const void* ws,
+                    const float* bs, void* skip, int lds, cudaStream_t s) {
   if (plan.Mp <= 0) return DS_OK;
   DS_CHECK(plan.pair_rows != nullptr, DS_ERR_INVALID, "edge_ffn: plan has no pair-row table");
   static bool attr_set[64] = {};            // the attribute is per device: one flag per device ordinal
@@ -388,9 +439,15 @@ int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ld
     DS_CUDA_CHECK(cudaFuncSetAttribute(edge_ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set[ctx->device & 63] = true;
   }
-  CUtensorMap tmW3, tmW4;
+  CUtensorMap tmW3, tmW4, tmWs;
   DS_TRY(ds_make_tmap_2d(ctx, &tmW3, w3, 128, 64, 64, 64, 128, false));
   DS_TRY(ds_make_tmap_2d(ctx, &tmW4, w4, 64, 128, 128, 64, 64, false));
+  tmWs = tmW3;
+  if (ws != nullptr) {
+    DS_CHECK(bs != nullptr && skip != nullptr && (lds % 8) == 0 && (reinterpret_cast<uintptr_t>(skip) & 15) == 0, DS_ERR_INVALID,
+             "edge_ffn: skip output needs a bias, a 16-byte aligned destination and a row stride that is a multiple of 8");
+    DS_TRY(ds_make_tmap_2d(ctx, &tmWs, ws, 16, 64, 64, 64, 16, false));
+  }
   EdgeFfnArgs a;
   a.e = e;
   a.xe = reinterpret_cast<bf16*>(xe);
@@ -402,13 +459,16 @@ int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ld
   a.pair_rows = plan.pair_rows;
   a.b3 = b3;
   a.b4 = b4;
+  a.bs = ws != nullptr ? bs : nullptr;
+  a.skip = reinterpret_cast<bf16*>(skip);
+  a.lds = lds;
   a.Mp = plan.Mp;
   const int tiles = (plan.Mp + TM - 1) / TM;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   if (ctx->ffn_variant == 1) {
-    ds_launch(edge_ffn_kernel<true>, dim3(grid), dim3(kThreads), kSmem, s, tmW3, tmW4, a);
+    ds_launch(edge_ffn_kernel<true>, dim3(grid), dim3(kThreads), kSmem, s, tmW3, tmW4, tmWs, a);
   } else {
-    ds_launch(edge_ffn_kernel<false>, dim3(grid), dim3(kThreads), kSmem, s, tmW3, tmW4, a);
+    ds_launch(edge_ffn_kernel<false>, dim3(grid), dim3(kThreads), kSmem, s, tmW3, tmW4, tmWs, a);
   }
   DS_CUDA_CHECK(cudaGetLastError());
   ctx->launch_count++;

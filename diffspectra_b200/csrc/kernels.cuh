@@ -174,8 +174,10 @@ int coord_mod_launch(DsContext* ctx, int B, int n_blocks, const float* ada, void
 int umma2_probe_launch(DsContext* ctx, const void* A, const void* W, float* out, int K, cudaStream_t s);
 
 // fused edge-stream update of one block (edge_ffn_tc.cu): residual + LN + modulate -> ff3 -> SiLU -> ff4 -> gated residual
+// ws / bs / skip / lds: optional skip projection edge_l(e) [64 -> 16] of the updated rows into the edge-head operand (null: none)
 int edge_ffn_launch(DsContext* ctx, const Plan& plan, float* e, void* xe, int ldx, const float* pn, const float* n2e_b,
-                    const float* ada_l, const void* w3, const float* b3, const void* w4, const float* b4, cudaStream_t s);
+                    const float* ada_l, const void* w3, const float* b3, const void* w4, const float* b4, const void* ws,
+                    const float* bs, void* skip, int lds, cudaStream_t s);
 
 int launch_pack_dense(DsContext* ctx, const Plan& plan, const float* x, const float* ex, float* xs, float* es,
                       cudaStream_t s);

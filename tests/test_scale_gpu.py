@@ -106,14 +106,14 @@ def test_fused_kernels_match_split_path(monkeypatch):
     nm, em, x, ex, cx, cex, nl = _inputs(n, 29, seed=41)
     ctx = W.synthetic_spectra(64, version, seed=6).cuda()
     outs = []
-    for mask in ('15', '31', '79'):
+    for mask in ('15', '31', '79', '335'):          # 335 = 79 + 256: skip projection as a third MMA of the fused edge stream
         monkeypatch.setenv('DS_FUSE_MASK', mask)            # read by ds_create
         model = build_model(version, salt=4, coord_scale=0.02, precision='bf16', min_rbf_std=0.3)
         with torch.no_grad():
             outs.append(model(nl, x, nm, em, context=ctx, edge_x=ex, noise_level=nl, cond_x=cx, cond_edge_x=cex))
-    for mask, alt in zip(('31', '79'), outs[1:]):
+    for mask, alt in zip(('31', '79', '335'), outs[1:]):
         e_pos, e_atom, e_edge = rel_l2(alt[0][..., :3], outs[0][0][..., :3]), rel_l2(alt[0][..., 3:], outs[0][0][..., 3:]), rel_l2(alt[1], outs[0][1])
         print('DS_FUSE_MASK=%s vs 15: pos %.2e atom %.2e edge %.2e' % (mask, e_pos, e_atom, e_edge))
         # the fused coordinate head rounds G + A + B to bf16 at other points than gp GEMM + k_coord_ln do: bf16-level differences
         assert e_pos < (2e-3 if mask == '31' else 1e-4)
-        assert e_atom < 2e-3 and e_edge < 2e-3
+        assert e_atom < 4e-3 and e_edge < 2e-3
