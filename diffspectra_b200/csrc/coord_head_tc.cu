@@ -390,7 +390,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0, q4 = q0, q5 = q0;     // two chains per output
       uint32_t eacc[2][16];
       ptx::tmem_ld16_nowait(t_acc, eacc[0]);
-#pragma unroll 2
+#pragma unroll 4
       for (int c = 0; c < 128; c += 16) {
         uint32_t (&acc)[16] = eacc[(c >> 4) & 1];
         ptx::tmem_wait_ld16(acc);

