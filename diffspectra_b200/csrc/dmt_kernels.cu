@@ -78,6 +78,9 @@ __global__ void __launch_bounds__(256) k_time_feat(const float* __restrict__ nl,
 
 // ----------------------------------------------------------------------------- root embeddings
 // h = node_emb([h(6) | cond_h(6)])  (dmt.py:343-345,376); pos = x[:, :3]
+// 16 atoms per CTA: thread t owns output channel t and keeps its 12 weights in registers (one CTA per atom was bound by
+// the launch of 18.5 k tiny blocks: 37.5 us for 38 MB of output)
+constexpr int kRootAtoms = 16;
 template <typename AT>
 __global__ void __launch_bounds__(256) k_root_nodes(int Mn, const float* __restrict__ xs, const float* __restrict__ cond,
                                                     const float* __restrict__ w, const float* __restrict__ b,
@@ -85,19 +88,35 @@ __global__ void __launch_bounds__(256) k_root_nodes(int Mn, const float* __restr
                                                     float* __restrict__ pos) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float in[12];
-  const int m = blockIdx.x;
+  __shared__ float in[kRootAtoms][12];
+  const int m0 = blockIdx.x * kRootAtoms;
   const int t = threadIdx.x;
-  if (t < 6) in[t] = xs[m * 9 + 3 + t];
-  else if (t < 12) in[t] = cond ? cond[m * 9 + 3 + (t - 6)] : 0.f;
-  if (t < 3) pos[m * 3 + t] = xs[m * 9 + t];
-  __syncthreads();
-  float acc = b[t];
+  if (t < kRootAtoms * 12) {
+    const int a = t / 12, k = t - a * 12, m = m0 + a;
+    float v = 0.f;
+    if (m < Mn) v = k < 6 ? xs[m * 9 + 3 + k] : (cond ? cond[m * 9 + 3 + (k - 6)] : 0.f);
+    in[a][k] = v;
+  }
+  if (t < kRootAtoms * 3 && m0 * 3 + t < Mn * 3) {
+    const int a = t / 3, c = t - a * 3;
+    pos[(m0 + a) * 3 + c] = xs[(m0 + a) * 9 + c];
+  }
+  float wr[12];
 #pragma unroll
-  for (int k = 0; k < 12; ++k) acc = fmaf(w[t * 12 + k], in[k], acc);
-  h[static_cast<size_t>(m) * D_NODE + t] = acc;
-  hb[static_cast<size_t>(m) * D_NODE + t] = from_f32<AT>(acc);
-  ahid[static_cast<size_t>(m) * 768 + t] = from_f32<AT>(acc);
+  for (int k = 0; k < 12; ++k) wr[k] = w[t * 12 + k];
+  const float bias = b[t];
+  __syncthreads();
+#pragma unroll 4
+  for (int a = 0; a < kRootAtoms; ++a) {
+    const int m = m0 + a;
+    if (m >= Mn) break;
+    float acc = bias;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc = fmaf(wr[k], in[a][k], acc);
+    h[static_cast<size_t>(m) * D_NODE + t] = acc;
+    hb[static_cast<size_t>(m) * D_NODE + t] = from_f32<AT>(acc);
+    ahid[static_cast<size_t>(m) * 768 + t] = from_f32<AT>(acc);
+  }
 }
 
 // adjacency heads from the self-conditioning inputs (dmt.py:337-340, models/utils.py:118-126) and the
@@ -529,6 +548,39 @@ template <typename T>
 __device__ __forceinline__ void store8(T* row, int lane, const float (&v)[8]) {
   store4<T>(row + 4 * lane, v[0], v[1], v[2], v[3]);
   store4<T>(row + 128 + 4 * lane, v[4], v[5], v[6], v[7]);
+}
+
+// Sampling loop: every molecule of the batch is at the same noise level, so time_mlp (sinusoidal features -> Linear -> GELU ->
+// Linear, dmt.py:249-257,353) is computed for ONE row; only the spectral context differs per molecule (dmt.py:354):
+//   t3[o] = time_mlp.3(feat)[o]          (warp per output, K = 1024)
+//   s[b, o] = SiLU(t3[o] + ctx[b, o])    (the operand of the adaLN projection)
+template <typename AT>
+__global__ void __launch_bounds__(256) k_time_gemv(const AT* __restrict__ feat, const AT* __restrict__ w, const float* __restrict__ b,
+                                                   float* __restrict__ t3) {
+  pdl_trigger();
+  pdl_wait();
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const AT* wr = w + static_cast<size_t>(o) * D_TIME;
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < D_TIME; k += 128) {
+    const float4 f = load4<AT>(feat + k + 4 * lane), ww = load4<AT>(wr + k + 4 * lane);
+    acc = fmaf(f.x, ww.x, acc); acc = fmaf(f.y, ww.y, acc); acc = fmaf(f.z, ww.z, acc); acc = fmaf(f.w, ww.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) t3[o] = acc + b[o];
+}
+template <typename AT, bool kFast>
+__global__ void __launch_bounds__(256) k_time_bcast(int B, const float* __restrict__ t3, const float* __restrict__ ctx, AT* __restrict__ s_act) {
+  pdl_trigger();
+  pdl_wait();
+  const int idx = blockIdx.x * 256 + threadIdx.x;          // one thread per 4 outputs
+  if (idx >= B * (D_TIME / 4)) return;
+  const int c = (idx & (D_TIME / 4 - 1)) * 4;
+  const float4 t = *reinterpret_cast<const float4*>(t3 + c);
+  const float4 x = *reinterpret_cast<const float4*>(ctx + static_cast<size_t>(idx) * 4);
+  store4<AT>(s_act + static_cast<size_t>(idx) * 4, act_silu<kFast>(t.x + x.x), act_silu<kFast>(t.y + x.y), act_silu<kFast>(t.z + x.z),
+             act_silu<kFast>(t.w + x.w));
 }
 
 // hh = modulate(LN(h), nsh1, nsc1)   (dmt.py:148)
@@ -1191,15 +1243,26 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
   ds_launch(k_zero_flags, dim3(1), dim3(32), 0, s, w.flags);
   LAUNCH_CHECK(ctx);
   // time embedding (+ cached spectral context) -> SiLU -> per-molecule adaLN table
-  ds_launch(k_time_feat<AT>, dim3(B), dim3(256), 0, s, noise_level, sr, pw.tm_freq, pw.tm1_w, pw.tm1_b, reinterpret_cast<AT*>(w.tfeat));
-  LAUNCH_CHECK(ctx);
-  DS_TRY(linear(ctx, w.tfeat, D_TIME, pw.tm3_w, D_TIME, pw.tm3_b, ctx_emb, D_TIME, w.s_act, D_TIME, AD, B, D_TIME, D_TIME,
-                ACT_SILU, s));
+  if (kFast && noise_level == nullptr) {
+    // sampling loop: one noise level for the whole batch -> the time MLP once, then broadcast + context + SiLU
+    ds_launch(k_time_feat<AT>, dim3(1), dim3(256), 0, s, noise_level, sr, pw.tm_freq, pw.tm1_w, pw.tm1_b, reinterpret_cast<AT*>(w.tfeat));
+    LAUNCH_CHECK(ctx);
+    float* t3 = reinterpret_cast<float*>(w.f2);          // [1024] scratch (the node FFN buffer is not live yet)
+    ds_launch(k_time_gemv<AT>, dim3(D_TIME / 8), dim3(256), 0, s, reinterpret_cast<const AT*>(w.tfeat), reinterpret_cast<const AT*>(pw.tm3_w), pw.tm3_b, t3);
+    LAUNCH_CHECK(ctx);
+    ds_launch(k_time_bcast<AT, kFast>, dim3(cdiv(B * (D_TIME / 4), 256)), dim3(256), 0, s, B, t3, ctx_emb, reinterpret_cast<AT*>(w.s_act));
+    LAUNCH_CHECK(ctx);
+  } else {
+    ds_launch(k_time_feat<AT>, dim3(B), dim3(256), 0, s, noise_level, sr, pw.tm_freq, pw.tm1_w, pw.tm1_b, reinterpret_cast<AT*>(w.tfeat));
+    LAUNCH_CHECK(ctx);
+    DS_TRY(linear(ctx, w.tfeat, D_TIME, pw.tm3_w, D_TIME, pw.tm3_b, ctx_emb, D_TIME, w.s_act, D_TIME, AD, B, D_TIME, D_TIME,
+                  ACT_SILU, s));
+  }
   DS_TRY(linear(ctx, w.s_act, D_TIME, pw.w_ada, D_TIME, pw.b_ada, nullptr, 0, w.ada, ADA_LD, DT_F32, B, ADA_LD, D_TIME,
                 ACT_NONE, s));
   if (kFast && (ctx->fuse_mask & 16) && Mp > 0) DS_TRY(coord_mod_launch(ctx, B, N_LAYERS, w.ada, w.cmod, s));
   // root embeddings
-  ds_launch(k_root_nodes<AT>, dim3(Mn), dim3(256), 0, s, Mn, xs, cond_x, pw.node_emb_w, pw.node_emb_b, w.h, reinterpret_cast<AT*>(w.hb),
+  ds_launch(k_root_nodes<AT>, dim3(cdiv(Mn, kRootAtoms)), dim3(256), 0, s, Mn, xs, cond_x, pw.node_emb_w, pw.node_emb_b, w.h, reinterpret_cast<AT*>(w.hb),
                                       reinterpret_cast<AT*>(w.ahid), w.pos);
   LAUNCH_CHECK(ctx);
   if (Mp > 0) {

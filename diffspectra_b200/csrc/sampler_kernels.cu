@@ -37,20 +37,7 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   return make_float2(r * cs, r * sn);
 }
 constexpr uint32_t TAG_NODE = 0x4e4f4445u, TAG_EDGE = 0x45444745u;
-// 9 raw normals of atom a of global molecule gid at draw index `step` (step = -1 -> 0xffffffff: initial noise)
-__device__ __forceinline__ void philox_node(unsigned long long seed, long long gid, int step, int a, float (&z)[9]) {
-  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(a + 64 * q), static_cast<uint32_t>(step),
-                                             static_cast<uint32_t>(gid), TAG_NODE ^ static_cast<uint32_t>(gid >> 32)), key);
-    const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
-    if (q * 4 + 0 < 9) z[q * 4 + 0] = n0.x;
-    if (q * 4 + 1 < 9) z[q * 4 + 1] = n0.y;
-    if (q * 4 + 2 < 9) z[q * 4 + 2] = n1.x;
-    if (q * 4 + 3 < 9) z[q * 4 + 3] = n1.y;
-  }
-}
+// draw index `step` (step = -1 -> 0xffffffff: initial noise); atoms: call q of atom a = counter word a + 64 q (philox_node_quad)
 __device__ __forceinline__ float2 philox_pair(unsigned long long seed, long long gid, int step, int i, int j) {
   const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
   const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(i * 64 + j), static_cast<uint32_t>(step),
@@ -105,61 +92,78 @@ __global__ void k_unpack_pairs(Plan plan, const float* __restrict__ es, float* _
 }
 
 // ----------------------------------------------------------------------------- ancestral update
-// nodes: x <- c_x x + c_pred pred + sigma T eps,  eps = [CoM-free masked N(0,1)^3 | masked N(0,1)^6]
-// one warp per molecule (atoms lane, lane+32)                                  sampling.py:605-612
-__global__ void __launch_bounds__(256) k_sampler_nodes(Plan plan, float* __restrict__ xs, const float* __restrict__ pred,
-                                                       float* __restrict__ xmean, StepRef sr, int step_host, NoiseSrc ns,
-                                                       float temperature, int init_only) {
+// nodes: x <- c_x x + c_pred pred + sigma T eps,  eps = [CoM-free masked N(0,1)^3 | masked N(0,1)^6]      sampling.py:605-612
+// One CTA of three warps per molecule: warp q owns channels [4q, 4q+4) (= the q-th Philox call of an atom: pos xyz + h0 |
+// h1..h4 | h5), lanes are atoms (lane, lane + 32).  The centre of mass only involves warp 0.  (One warp per molecule did
+// all nine channels of an atom in one thread: 1024 warps of ~600 dependent instructions each on 148 SMs, 26 us per step.)
+__device__ __forceinline__ void philox_node_quad(unsigned long long seed, long long gid, int step, int a, int q, float (&z)[4]) {
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(a + 64 * q), static_cast<uint32_t>(step), static_cast<uint32_t>(gid),
+                                           TAG_NODE ^ static_cast<uint32_t>(gid >> 32)), key);
+  const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+  z[0] = n0.x; z[1] = n0.y; z[2] = n1.x; z[3] = n1.y;
+}
+__global__ void __launch_bounds__(96) k_sampler_nodes(Plan plan, float* __restrict__ xs, const float* __restrict__ pred,
+                                                      float* __restrict__ xmean, StepRef sr, int step_host, NoiseSrc ns,
+                                                      float temperature, int init_only) {
   pdl_trigger();
   pdl_wait();
-  const int mol = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (mol >= plan.B) return;
+  const int mol = blockIdx.x, q = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = plan.n_atoms[mol], base = plan.noff[mol];
   const int step = sr.step ? *sr.step : step_host;
-  float z[2][9];
+  const int nch = q == 2 ? 1 : 4;                 // channels of this warp: c = 4 q + k
+  float z[2][4];
   float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int a = lane + 32 * q;
+  for (int hq = 0; hq < 2; ++hq) {
+    const int a = lane + 32 * hq;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) z[q][c] = 0.f;
+    for (int k = 0; k < 4; ++k) z[hq][k] = 0.f;
     if (a < n) {
       if (ns.raw_pos) {
         const size_t so = static_cast<size_t>(init_only ? 0 : step - ns.raw_step_base) * plan.B * plan.N;
         const float* rp = ns.raw_pos + (so + static_cast<size_t>(mol) * plan.N + a) * 3;
         const float* rh = ns.raw_h + (so + static_cast<size_t>(mol) * plan.N + a) * 6;
-        z[q][0] = rp[0]; z[q][1] = rp[1]; z[q][2] = rp[2];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) z[q][3 + c] = rh[c];
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * q + k;
+          if (c < 9) z[hq][k] = c < 3 ? rp[c] : rh[c - 3];
+        }
       } else {
-        philox_node(ns.seed, ns.gid_base + mol, init_only ? -1 : step + ns.philox_step_offset, a, z[q]);
+        philox_node_quad(ns.seed, ns.gid_base + mol, init_only ? -1 : step + ns.philox_step_offset, a, q, z[hq]);
       }
-      sx += z[q][0]; sy += z[q][1]; sz += z[q][2];
+      if (q == 0) { sx += z[hq][0]; sy += z[hq][1]; sz += z[hq][2]; }
     }
   }
-  const float fn = static_cast<float>(n);
-  const float mx = warp_sum(sx) / fn, my = warp_sum(sy) / fn, mz = warp_sum(sz) / fn;
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  if (q == 0) {                                   // warp-uniform
+    const float fn = static_cast<float>(n);
+    mx = warp_sum(sx) / fn; my = warp_sum(sy) / fn; mz = warp_sum(sz) / fn;
+  }
   float cx = 0.f, cp = 0.f, sg = 1.f;
   if (!init_only) {
     cx = sr.coef[step * 4 + 0]; cp = sr.coef[step * 4 + 1]; sg = sr.coef[step * 4 + 2];
   }
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int a = lane + 32 * q;
+  for (int hq = 0; hq < 2; ++hq) {
+    const int a = lane + 32 * hq;
     if (a >= n) continue;
-    z[q][0] -= mx; z[q][1] -= my; z[q][2] -= mz;
-    float* xr = xs + static_cast<size_t>(base + a) * 9;
+    if (q == 0) { z[hq][0] -= mx; z[hq][1] -= my; z[hq][2] -= mz; }
+    float* xr = xs + static_cast<size_t>(base + a) * 9 + 4 * q;
     if (init_only) {
 #pragma unroll
-      for (int c = 0; c < 9; ++c) xr[c] = z[q][c];
+      for (int k = 0; k < 4; ++k)
+        if (k < nch) xr[k] = z[hq][k];
     } else {
-      const float* pr = pred + static_cast<size_t>(base + a) * 9;
-      float* xm = xmean + static_cast<size_t>(base + a) * 9;
+      const float* pr = pred + static_cast<size_t>(base + a) * 9 + 4 * q;
+      float* xm = xmean + static_cast<size_t>(base + a) * 9 + 4 * q;
 #pragma unroll
-      for (int c = 0; c < 9; ++c) {
-        const float mean = cx * xr[c] + cp * pr[c];
-        xm[c] = mean;
-        xr[c] = mean + (sg * z[q][c]) * temperature;
+      for (int k = 0; k < 4; ++k) {
+        if (k < nch) {
+          const float mean = cx * xr[k] + cp * pr[k];
+          xm[k] = mean;
+          xr[k] = mean + (sg * z[hq][k]) * temperature;
+        }
       }
     }
   }
@@ -340,7 +344,7 @@ int launch_unpack_dense(DsContext* ctx, const Plan& plan, const float* xs, const
 int launch_sampler_step(DsContext* ctx, const Plan& plan, float* xs, float* es, const float* pred_x, const float* pred_e,
                         float* xmean, float* emean, StepRef sr, int step_host, const NoiseSrc& ns, float temperature,
                         cudaStream_t s) {
-  ds_launch(k_sampler_nodes, dim3(cdiv(plan.B, 8)), dim3(256), 0, s, plan, xs, pred_x, xmean, sr, step_host, ns, temperature, 0);
+  ds_launch(k_sampler_nodes, dim3(plan.B), dim3(96), 0, s, plan, xs, pred_x, xmean, sr, step_host, ns, temperature, 0);
   LAUNCH_CHECK(ctx);
   if (plan.Mp > 0) {
     ds_launch(k_sampler_pairs, dim3(cdiv(plan.Mp, 256)), dim3(256), 0, s, plan, es, pred_e, emean, sr, step_host, ns, temperature, 0);
@@ -351,7 +355,7 @@ int launch_sampler_step(DsContext* ctx, const Plan& plan, float* xs, float* es, 
 
 int launch_init_noise(DsContext* ctx, const Plan& plan, float* xs, float* es, const NoiseSrc& ns, cudaStream_t s) {
   StepRef sr{nullptr, nullptr};
-  ds_launch(k_sampler_nodes, dim3(cdiv(plan.B, 8)), dim3(256), 0, s, plan, xs, nullptr, nullptr, sr, 0, ns, 1.0f, 1);
+  ds_launch(k_sampler_nodes, dim3(plan.B), dim3(96), 0, s, plan, xs, nullptr, nullptr, sr, 0, ns, 1.0f, 1);
   LAUNCH_CHECK(ctx);
   if (plan.Mp > 0) {
     ds_launch(k_sampler_pairs, dim3(cdiv(plan.Mp, 256)), dim3(256), 0, s, plan, es, nullptr, nullptr, sr, 0, ns, 1.0f, 1);
