@@ -262,6 +262,7 @@ struct GemmDesc {
   int ldres = 0;
   void* out2 = nullptr;                 // RESGATE bf16 copy [M, ldo2]
   int ldo2 = 0;
+  int split_n = 0;                      // STORE (bf16, TMA out): output columns >= split_n go to out2 (ld ldo2) instead, 0 = off
   const float* wc2 = nullptr;           // COORD: coord_mlp.2 [3,256]
   const uint8_t* pflags = nullptr;      // COORD: adjacency bits per pair
   float* wdir = nullptr;                // COORD: output per directed edge

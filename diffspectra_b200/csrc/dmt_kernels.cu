@@ -1289,7 +1289,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
 
   const int ngrp = (plan.N + ATT_G - 1) / ATT_G;
   uint8_t* dflags = w.pflags + (Mp > 0 ? Mp : 1);      // adjacency bits per directed edge (source-major order)
-  if (kFast && (ctx->fuse_mask & 32) && Mp > 0) {
+  if (kFast && (ctx->fuse_mask & 32) && !(ctx->fuse_mask & 16) && Mp > 0) {      // only the split coordinate head reads them
     ds_launch(k_dir_flags, dim3(cdiv(Md, 256)), dim3(256), 0, s, Md, plan.dir_info, w.pflags, dflags);
     LAUNCH_CHECK(ctx);
   }
@@ -1385,11 +1385,21 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       ds_launch(k_node_update2<AT>, dim3(cdiv(Mn, 8)), dim3(256), 0, sn, plan, w.h1, w.f2, w.ada, l, w.h, reinterpret_cast<AT*>(w.hb));
       LAUNCH_CHECK(ctx);
     }
-    if (Mp > 0)
-      DS_TRY(linear(ctx, w.hb, 256, bw.wab, 256, bw.bab, nullptr, 0, w.ab, 512, AD, Mn, 512, 256, ACT_NONE, sn));
-    // skip connection into the atom head (dmt.py:387-388)
-    DS_TRY(linear(ctx, w.hb, 256, bw.node_w, 256, bw.node_b, nullptr, 0, reinterpret_cast<AT*>(w.ahid) + 256 + 64 * l, 768,
-                  AD, Mn, 64, 256, ACT_NONE, sn));
+    if (kFast && Mp > 0) {
+      // hoisted h_row | h_col parts of input_lin AND the skip projection into the atom head (dmt.py:387-388) as ONE GEMM over
+      // the updated rows: output columns [0, 512) -> ab, [512, 576) -> the block's 64 columns of the atom-head operand
+      GemmDesc g;
+      g.A = w.hb; g.lda = 256; g.W = bw.wab; g.ldw = 256; g.bias = bw.bab; g.out = w.ab; g.ldo = 512; g.M = Mn; g.N = 576; g.K = 256;
+      g.a_dtype = DT_BF16; g.out_dtype = DT_BF16; g.mode = GEMM_STORE; g.split_n = 512;
+      g.out2 = reinterpret_cast<AT*>(w.ahid) + 256 + 64 * l; g.ldo2 = 768;
+      DS_TRY(gemm_tc_launch(ctx, g, sn));
+    } else {
+      if (Mp > 0)
+        DS_TRY(linear(ctx, w.hb, 256, bw.wab, 256, bw.bab, nullptr, 0, w.ab, 512, AD, Mn, 512, 256, ACT_NONE, sn));
+      // skip connection into the atom head (dmt.py:387-388)
+      DS_TRY(linear(ctx, w.hb, 256, bw.node_w, 256, bw.node_b, nullptr, 0, reinterpret_cast<AT*>(w.ahid) + 256 + 64 * l, 768,
+                    AD, Mn, 64, 256, ACT_NONE, sn));
+    }
     if (Mp > 0) {
       // ---- pair chain B: residual + LN -> FFN -> residual; pair part of input_lin; skip projection
       ctx->cta_cap = ecap;

@@ -66,6 +66,7 @@ struct Epi {
   const uint8_t* pflags;
   float* wdir;
   int out2_present;
+  int split_n;          // STORE + TMA_OUT: column tiles at n0 >= split_n are stored through the second map (0 = off)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -337,7 +338,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if (n0 + c < N && m0 + wq * 32 < M) tma_store_2d(&tmO, box, n0 + c, m0 + wq * 32);
+              if (n0 + c < N && m0 + wq * 32 < M) {
+                if (ep.split_n > 0 && n0 >= ep.split_n) tma_store_2d(&tmR, box, n0 + c - ep.split_n, m0 + wq * 32);   // second destination
+                else tma_store_2d(&tmO, box, n0 + c, m0 + wq * 32);
+              }
               tma_store_commit();
             }
             sb ^= 1;
@@ -532,7 +536,15 @@ int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
     if (g.resid) DS_TRY(make_tmap(ctx, &tmR, g.resid, g.M, g.N, g.ldres, 32, 32, true));
     if (g.out2) DS_TRY(make_tmap(ctx, &tmO, g.out2, g.M, g.N, g.ldo2, 64, 32));
   } else if (TMA_OUT) {
-    DS_TRY(make_tmap(ctx, &tmO, g.out, g.M, g.N, g.ldo, 64, 32));
+    if (g.split_n > 0) {      // two destinations: columns [0, split_n) -> out, [split_n, N) -> out2
+      DS_CHECK(MODE == GEMM_STORE && g.out2 != nullptr && (g.split_n % BN) == 0 && ((g.N - g.split_n) % 8) == 0 && (g.ldo2 % 8) == 0 &&
+                   (reinterpret_cast<uintptr_t>(g.out2) & 15) == 0,
+               DS_ERR_INVALID, "gemm_tc: split output needs split_n on a column-tile boundary and a 16-byte aligned second destination");
+      DS_TRY(make_tmap(ctx, &tmO, g.out, g.M, g.split_n, g.ldo, 64, 32));
+      DS_TRY(make_tmap(ctx, &tmR, g.out2, g.M, g.N - g.split_n, g.ldo2, 64, 32));
+    } else {
+      DS_TRY(make_tmap(ctx, &tmO, g.out, g.M, g.N, g.ldo, 64, 32));
+    }
   }
   Epi ep;
   ep.bias = g.bias; ep.addmat = g.addmat; ep.out = g.out; ep.ldo = g.ldo; ep.ldadd = g.ldadd;
@@ -540,6 +552,7 @@ int launch_cfg(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
   ep.row_info = g.row_info; ep.info_shift = g.info_shift; ep.ada = g.ada; ep.off_a = g.off_a; ep.off_b = g.off_b;
   ep.resid = g.resid; ep.ldres = g.ldres; ep.wc2 = g.wc2; ep.pflags = g.pflags; ep.wdir = g.wdir;
   ep.out2_present = g.out2 != nullptr;
+  ep.split_n = (TMA_OUT && MODE == GEMM_STORE) ? g.split_n : 0;
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int sms = (ctx->cta_cap > 0 && ctx->cta_cap < ctx->num_sms) ? ctx->cta_cap : ctx->num_sms;
@@ -595,6 +608,7 @@ int gemm_tc_launch(DsContext* ctx, const GemmDesc& g, cudaStream_t s) {
   // TMA stores clip the inner dimension at 16-byte granularity (measured): N must be a multiple of 8 bf16
   const bool tma_out = g.out_dtype == DT_BF16 && g.N >= 64 && (g.N % 8) == 0 && (g.ldo % 8) == 0 &&
                        (reinterpret_cast<uintptr_t>(g.out) & 15) == 0;
+  DS_CHECK(g.split_n == 0 || (tma_out && g.N > 128), DS_ERR_INVALID, "gemm_tc: split output is implemented for the bf16 TMA-store path with 256-column tiles");
   if (g.N <= 16) return launch_cfg<16, GEMM_STORE, false>(ctx, g, s);
   if (g.N <= 32) return launch_cfg<32, GEMM_STORE, false>(ctx, g, s);
   if (g.N <= 64) return tma_out ? launch_cfg<64, GEMM_STORE, true>(ctx, g, s) : launch_cfg<64, GEMM_STORE, false>(ctx, g, s);

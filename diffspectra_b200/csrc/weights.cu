@@ -213,11 +213,16 @@ int build(Packer& P, PackedWeights& pw) {
     P.copy(wil ? wil + 576 : nullptr, 640, we, 0, 128, 256, 64, true);    // dist columns first
     P.copy(wil ? wil + 512 : nullptr, 640, we, 64, 128, 256, 64, true);   // then e columns
     b.we = we;
-    void* wab = P.alloc_act(512 * 256);
-    float* bab = P.alloc_f32(512);
+    // rows 0..511: h_row | h_col parts of input_lin; rows 512..575: the block's skip projection node_l (dmt.py:387-388), so
+    // that ONE GEMM over the updated atom rows produces both (the skip columns go to the atom-head operand)
+    void* wab = P.alloc_act(576 * 256);
+    float* bab = P.alloc_f32(576);
     P.copy(wil, 640, wab, 0, 256, 256, 256, true);
     P.copy(wil ? wil + 256 : nullptr, 640, wab, 256 * 256, 256, 256, 256, true);
     P.copy(P.get(p + "equi_update.input_lin.bias"), 256, bab, 0, 256, 1, 256, false);
+    snprintf(buf, sizeof(buf), "node_%d", l);
+    P.copy(P.get(std::string(buf) + ".weight"), 256, wab, 512 * 256, 256, 64, 256, true);
+    P.copy(P.get(std::string(buf) + ".bias"), 64, bab, 512, 64, 1, 64, false);
     b.wab = wab;
     b.bab = bab;
     // bf16 mode: coord_mlp.0 is stored halved (exact in bf16) so that its SiLU is h + h tanh(h) (ACT_SILU_HALF)
