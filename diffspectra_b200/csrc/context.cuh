@@ -23,6 +23,7 @@ struct DsContext {
                                      // throughput-, not latency-bound, so a branch only takes SMs away from the pair chain
   int edge_cap = 124, node_cap = 24;
   int att_g = 4;                     // DS_ATT_G: targets (= warps) per attention CTA; 4 -> 128-thread CTAs, 12 per SM: 82.1 us vs 84.4 us with 8 (finer tail); 2 targets / 64 threads measured 84.7 us
+  int att_p1 = 1;                    // DS_ATT_P1: 1 = source-major pass 1 of the attention (a thread owns (source, head) and walks the targets)
   int ffn_variant = 1;               // DS_FFN: 1 = the pre-LayerNorm row is built cooperatively while the tile is staged (55.6 us), 0 = by the row's own thread (64.0 us)
   int cta_cap = 0;                   // cap applied to the next persistent-GEMM launches (0 = all SMs)
   cudaStream_t side_stream = nullptr;

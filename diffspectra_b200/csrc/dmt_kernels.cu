@@ -617,7 +617,7 @@ __device__ __forceinline__ uint4 ldg128_pinned(const void* p) {
   return v;
 }
 __device__ __forceinline__ float2 ld_pair2(const float* p) { return *reinterpret_cast<const float2*>(p); }
-template <typename AT, bool kFast, int MAXN, int G>
+template <typename AT, bool kFast, int MAXN, int G, bool kSrcMajor = false>
 __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int ngrp, const AT* __restrict__ qkv,
                                                        const AT* __restrict__ e01, const uint8_t* __restrict__ pflags,
                                                        float* __restrict__ hn, AT* __restrict__ hnb) {
@@ -648,6 +648,43 @@ __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int
   }
   __syncthreads();
   // pass 1: logits[jl][i][h] for source i -> target j
+  if constexpr (kSrcMajor && sizeof(AT) == 2) {
+    // source-major: a thread owns (source slot, head) and walks the group's targets, so the k row of a source is loaded ONCE
+    // for all targets of the CTA (it was re-read per target: a quarter of the pass's loads and L1 wavefronts), and no
+    // division is needed to decode the item index
+    const int hh = t & 15;
+    for (int i = t >> 4; i < n; i += 2 * G) {
+      __nv_bfloat162 kv[C_SUB / 2];
+      if (hh < N_SUB) {
+        const AT* kr = qkv + static_cast<size_t>(base + i) * QKV_LD + 256 + hh * 2;
+#pragma unroll
+        for (int d = 0; d < C_SUB / 2; ++d) kv[d] = *reinterpret_cast<const __nv_bfloat162*>(kr + QK_PAIR_STRIDE * d);
+      }
+      for (int jl = 0; jl < gsz; ++jl) {
+        const int row = srow[jl][i];
+        if (row < 0) continue;
+        if (hh < N_SUB) {
+          const AT* er = e01 + static_cast<size_t>(row) * E01_LD + hh * 2;
+          const float* qr = &sq[jl][hh * 2];
+          __nv_bfloat162 ev[C_SUB / 2];
+#pragma unroll
+          for (int d = 0; d < C_SUB / 2; ++d) ev[d] = *reinterpret_cast<const __nv_bfloat162*>(er + QK_PAIR_STRIDE * d);
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < C_SUB / 2; ++d) {
+            const float2 qv = *reinterpret_cast<const float2*>(qr + QK_PAIR_STRIDE * d);
+            const float2 ke = bf2_to_f2(__hmul2(ev[d], kv[d]));
+            a = fmaf(qv.x, ke.x, a);
+            a = fmaf(qv.y, ke.y, a);
+          }
+          slog[jl][i][2 + hh] = static_cast<LT>(a * 0.25f);   // 1 / sqrt(out_channels = 16)
+        } else {
+          const int bit = hh - N_SUB;                      // 0: adj2d, 1: adjsp
+          slog[jl][i][bit] = static_cast<LT>(((pflags[row] >> bit) & 1) ? 1.0f : -60000.0f);
+        }
+      }
+    }
+  } else {
   const unsigned rcp_n = 65536u / static_cast<unsigned>(n) + 1u;     // r / n == (r * rcp_n) >> 16 for r < 8 * 64
   for (int idx = t; idx < gsz * n * N_HEADS; idx += 32 * G) {
     const int hh = idx & 15, r = idx >> 4;
@@ -700,6 +737,7 @@ __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int
       const int bit = hh - N_SUB;                      // 0: adj2d, 1: adjsp
       slog[jl][i][bit] = static_cast<LT>(((pflags[row] >> bit) & 1) ? 1.0f : (kFast ? -60000.0f : -1e10f));   // exp() == 0 either way
     }
+  }
   }
   __syncthreads();
   // softmax over sources: one thread per (target, head), serial over sources (no shuffles, every lane busy)
@@ -1353,7 +1391,12 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
       const AT* qkv_ = reinterpret_cast<const AT*>(w.qkv);
       const AT* e01_ = reinterpret_cast<const AT*>(w.e01);
       AT* hnb_ = reinterpret_cast<AT*>(w.hnb);
-      if (ag == 4) {
+      if (ag == 4 && ctx->att_p1 == 1) {        // source-major pass 1 (k rows loaded once per CTA)
+        if (plan.N <= 32)
+          ds_launch(k_attention_grp<AT, kFast, 32, 4, true>, dim3(B * ngrp_a), dim3(128), 0, s, plan, ngrp_a, qkv_, e01_, w.pflags, w.hn, hnb_);
+        else
+          ds_launch(k_attention_grp<AT, kFast, 64, 4, true>, dim3(B * ngrp_a), dim3(128), 0, s, plan, ngrp_a, qkv_, e01_, w.pflags, w.hn, hnb_);
+      } else if (ag == 4) {
         if (plan.N <= 32)
           ds_launch(k_attention_grp<AT, kFast, 32, 4>, dim3(B * ngrp_a), dim3(128), 0, s, plan, ngrp_a, qkv_, e01_, w.pflags, w.hn, hnb_);
         else
