@@ -740,19 +740,25 @@ __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int
   }
   }
   __syncthreads();
-  // softmax over sources: one thread per (target, head), serial over sources (no shuffles, every lane busy)
-  if (t < gsz * N_HEADS) {
-    const int jl = t >> 4, hh = t & 15, j = j0 + jl;
-    float mx = -INFINITY;
-    for (int i = 0; i < n; ++i)
-      if (i != j) mx = fmaxf(mx, static_cast<float>(slog[jl][i][hh]));
-    float den = 0.f;
-    for (int i = 0; i < n; ++i) {
-      const float ex = (i != j) ? act_exp<kFast>(static_cast<float>(slog[jl][i][hh]) - mx) : 0.f;
-      slog[jl][i][hh] = static_cast<LT>(ex);
-      den += ex;
+  // softmax over sources: warp w <-> target j0 + w, lane = head + 16 * half: the two halves of a warp take the even / odd
+  // sources of every (target, head) and meet through one shuffle each for the maximum and the denominator (one thread per
+  // (target, head) walking all sources twice was a serial fifth of the CTA's critical path with half the threads idle)
+  {
+    const int jl = t >> 5, hh = t & 15, half = (t >> 4) & 1, j = j0 + jl;
+    if (jl < gsz) {                                    // warp-uniform
+      float mx = -INFINITY;
+      for (int i = half; i < n; i += 2)
+        if (i != j) mx = fmaxf(mx, static_cast<float>(slog[jl][i][hh]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+      float den = 0.f;
+      for (int i = half; i < n; i += 2) {
+        const float ex = (i != j) ? act_exp<kFast>(static_cast<float>(slog[jl][i][hh]) - mx) : 0.f;
+        slog[jl][i][hh] = static_cast<LT>(ex);
+        den += ex;
+      }
+      den += __shfl_xor_sync(0xffffffffu, den, 16);
+      if (half == 0) sinv[jl][hh] = 1.0f / (den + 1e-16f);
     }
-    sinv[jl][hh] = 1.0f / (den + 1e-16f);
   }
   __syncthreads();
   // pass 2: messages; warp w <-> target j0 + w, lane <-> 8 value channels (one head per 2 lanes):
