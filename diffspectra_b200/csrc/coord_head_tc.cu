@@ -144,7 +144,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       ptx::mbar_init(&tmem_free[i], 16);      // one arrival per epilogue warp of both CTAs
     }
     ptx::mbar_init(win_full, 1);
-    ptx::mbar_init(win_free, 1);
+    ptx::mbar_init(win_free, 8);             // one arrival per build warp
     ptx::fence_barrier_init();
   }
   if (warp == 17) ptx::tmem_alloc_2sm<512>(tmem_slot);
@@ -251,16 +251,25 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint8_t* win = smem + OFF_WIN;
     const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
 #define DS_STAMP(k) do { if (stamp) a.dbg[it * 8 + (k)] = clock64(); } while (0)
+    // indices of the thread's edge one tile AHEAD: every dependent global load of a tile (per-atom rows, modulate vectors) then
+    // starts from registers, and its L1 prefetch is issued a whole pass earlier
+    auto load_idx = [&](int t, int2& rows_o, int& mol_o, int& alo_o) {
+      const int q0 = (cid + t * ncl) * TM;
+      const int pc = min(q0 + r, a.Mp - 1);
+      rows_o = __ldg(a.pair_rows + pc);
+      mol_o = __ldg(a.pair_info + pc) >> 12;
+      alo_o = __ldg(&a.pair_rows[min(q0, a.Mp - 1)].x);
+    };
+    int2 rows_n = make_int2(0, 0);
+    int mol_n = 0, alo_n = 0;
+    if (my_n > 0) load_idx(0, rows_n, mol_n, alo_n);
     for (int it = 0; it < my_n; ++it) {
       DS_STAMP(0);
       uint32_t yreg[64];          // the thread's 128 channels of y, packed bf16 pairs
       const int s = it & 1;
-      const int p0 = (cid + it * ncl) * TM;
-      const int p = p0 + r;
-      const int pc = p < a.Mp ? p : a.Mp - 1;
-      const int2 rows = __ldg(a.pair_rows + pc);
-      const int mol = __ldg(a.pair_info + pc) >> 12;
-      const int a_lo = __ldg(&a.pair_rows[min(p0, a.Mp - 1)].x);
+      const int2 rows = rows_n;
+      const int mol = mol_n, a_lo = alo_n;
+      if (it + 1 < my_n) load_idx(it + 1, rows_n, mol_n, alo_n);
       const bf16* cm = a.cmod + static_cast<size_t>(mol) * 512 + cb;
       // rank 0: edge i -> j: y = A[i] + B[j] + G;   rank 1: edge j -> i: y = A[j] + B[i] + G.  The atom that is (nearly)
       // uniform over the lanes of a warp is i, the lane-varying one j: its half-row comes from the window.
@@ -269,8 +278,15 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int wr = rows.y - a_lo;
       const bool in_win = wr >= 0 && wr < kWinRows;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(s * 256 + cb);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(urow));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(urow + 64));
+      if (it == 0) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(urow));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(urow + 64));
+      }
+      // the modulate vectors of this thread's channels are wanted by pass B, a whole pass A from here
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 64));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 256));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 320));
       wait_guard(&g_full[s], (it >> 1) & 1, 5, it);
       ptx::tc_fence_after();
       DS_STAMP(1);
@@ -315,14 +331,16 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
       sstat[hf * 128 + r] = make_float2(sum2.x + sum2.y, sq2.x + sq2.y);
-      // the modulate vectors of this thread's channels are wanted by pass B
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 64));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 256));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 320));
+      if (it + 1 < my_n) {               // the next tile's per-atom half-row (its indices arrived during pass A)
+        const bf16* un = a.ab + static_cast<size_t>(rows_n.x) * 512 + (rank ? 256 : 0) + cb;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(un));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(un + 64));
+      }
       ptx::tc_fence_before();            // this thread's reads of G precede the MMA2 that overwrites those columns
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (threadIdx.x == 0) ptx::mbar_arrive(win_free);          // every thread is done with the window
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(win_free);                 // this warp is done with the window
+      // the two threads of a row sit in warps w and w ^ 4: a 64-thread named barrier per warp pair, not one over all 8 warps
+      asm volatile("bar.sync %0, 64;" ::"r"(4 + wq) : "memory");
       const float2 mine = sstat[hf * 128 + r], other = sstat[(hf ^ 1) * 128 + r];
       const float mean = (mine.x + other.x) * (1.0f / 256.0f);
       const float is = rsqrtf(fmaxf((mine.y + other.y) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-6f);
@@ -414,16 +432,16 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       float s0 = (q0.x + q0.y) + (q3.x + q3.y), s1 = (q1.x + q1.y) + (q4.x + q4.y), s2 = (q2.x + q2.y) + (q5.x + q5.y);
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_free[s]), 0));     // this warp's columns are drained
+      if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(&tmem_free[s]), 0));      // this warp's columns are drained
       if (hf == 1) spart[r] = make_float4(s0, s1, s2, 0.f);
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(8 + wq) : "memory");       // warps w and w + 4 hold the two halves of a row
       if (hf == 0 && ok) {
         const float4 o = spart[r];
         s0 += o.x; s1 += o.y; s2 += o.z;
         const float a2 = (fl & 1) ? 1.f : 0.f, asp = (fl & 2) ? 1.f : 0.f;
         a.wdir[d_out] = (act_tanh<true>(s0) + act_tanh<true>(s1) * a2 + act_tanh<true>(s2) * asp) / 3.0f;
       }
-      asm volatile("bar.sync 2, 256;" ::: "memory");          // spart may be overwritten by the next tile
+      asm volatile("bar.sync %0, 64;" ::"r"(8 + wq) : "memory");       // spart may be overwritten by the next tile
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // warps 18, 19: their registers go to the build warps
