@@ -292,42 +292,41 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       DS_STAMP(1);
       wait_guard(win_full, it & 1, 6, it);
       DS_STAMP(2);
-      // ---- pass A: chunks of 16 channels; the TMEM load of chunk c+1 is in flight while chunk c is consumed
+      // ---- pass A: chunks of 8 channels; the TMEM load of chunk c+1 is in flight while chunk c is consumed.  (Chunks of 16
+      // spilled ~22 registers of y to local memory, whose L1 traffic equalled all the global loads of the kernel.)
       float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
-      uint32_t accb[2][16];
-      ptx::tmem_ld16_nowait(t_addr, accb[0]);
+      uint32_t accb[2][8];
+      ptx::tmem_ld8_nowait(t_addr, accb[0]);
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 16) {
-        uint32_t (&acc)[16] = accb[(c0 >> 4) & 1];
-        uint4 u[2], v[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) u[q] = ldg128(urow + c0 + q * 8);
+      for (int c0 = 0; c0 < 128; c0 += 8) {
+        uint32_t (&acc)[8] = accb[(c0 >> 3) & 1];
+        const uint4 u = ldg128(urow + c0);
+        uint4 v;
         if (in_win) {
           const uint8_t* wb = win + ((cb + c0) >> 6) * kWinBox + wr * 128;
           const int ch0 = ((cb + c0) & 63) >> 3;
-#pragma unroll
-          for (int q = 0; q < 2; ++q) v[q] = *reinterpret_cast<const uint4*>(wb + (((ch0 + q) ^ (wr & 7)) << 4));
+          v = *reinterpret_cast<const uint4*>(wb + ((ch0 ^ (wr & 7)) << 4));
         } else {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) v[q] = ldg128(vrow + c0 + q * 8);
+          v = ldg128(vrow + c0);
         }
-        ptx::tmem_wait_ld16(acc);
-        if (c0 + 16 < 128) ptx::tmem_ld16_nowait(t_addr + c0 + 16, accb[((c0 >> 4) + 1) & 1]);
+        ptx::tmem_wait_ld8(acc);
+        if (c0 + 8 < 128) ptx::tmem_ld8_nowait(t_addr + c0 + 8, accb[((c0 >> 3) + 1) & 1]);
+        // A + B as packed bf16 adds (both operands are bf16 already), then fp32: + G, statistics
+        const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          // A + B as packed bf16 adds (both operands are bf16 already), then fp32: + G, statistics
-          const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u[q]);
-          const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v[q]);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const __nv_bfloat162 ab2 = __hadd2(u2[k], v2[k]);
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(&ab2);
-            const float2 y2 = fadd2(make_float2(__uint_as_float(acc[q * 8 + 2 * k]), __uint_as_float(acc[q * 8 + 2 * k + 1])),
-                                    make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)));
-            sum2 = fadd2(sum2, y2);
-            sq2 = ffma2(y2, y2, sq2);
-            yreg[(c0 >> 1) + q * 4 + k] = pack2(y2.x, y2.y);
-          }
+        for (int k = 0; k < 4; ++k) {
+          const __nv_bfloat162 ab2 = __hadd2(u2[k], v2[k]);
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(&ab2);
+          const float2 y2 = fadd2(make_float2(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1])),
+                                  make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)));
+          // the statistics are those of the ROUNDED values (the ones pass B normalises); this also ties the pack to pass A:
+          // left free, ptxas sinks the 64 packs below the LayerNorm barrier and keeps y as fp32 pairs, spilling ~20 of them
+          const uint32_t yb = pack2(y2.x, y2.y);
+          const float2 yr = make_float2(__uint_as_float(yb << 16), __uint_as_float(yb & 0xffff0000u));
+          sum2 = fadd2(sum2, yr);
+          sq2 = ffma2(yr, yr, sq2);
+          yreg[(c0 >> 1) + k] = yb;
         }
       }
       sstat[hf * 128 + r] = make_float2(sum2.x + sum2.y, sq2.x + sq2.y);
@@ -353,27 +352,40 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       // each): y is bf16 already, the modulate vectors arrive as bf16 pairs, so nothing is unpacked or re-packed.  The
       // per-row factors rstd and -mean rstd are rounded to bf16 (a 2^-9 relative error of the row's scale).
       const __nv_bfloat162 is2 = __float2bfloat162_rn(is), nm2 = __float2bfloat162_rn(-mean * is);
+      // chunks of 16 channels with the loads of the next two chunks in flight (a batch of 64 channels at once forced ~20
+      // registers of y into local memory)
+      uint4 shq[3][2], scq[3][2];
 #pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {
-        uint4 shq[8], scq[8];
+      for (int pre = 0; pre < 2; ++pre) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          shq[q] = ldg128(cm + hb * 64 + q * 8);
-          scq[q] = ldg128(cm + 256 + hb * 64 + q * 8);
+        for (int q = 0; q < 2; ++q) {
+          shq[pre][q] = ldg128(cm + pre * 16 + q * 8);
+          scq[pre][q] = ldg128(cm + 256 + pre * 16 + q * 8);
+        }
+      }
+#pragma unroll
+      for (int ck = 0; ck < 8; ++ck) {
+        if (ck + 2 < 8) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            shq[(ck + 2) % 3][q] = ldg128(cm + (ck + 2) * 16 + q * 8);
+            scq[(ck + 2) % 3][q] = ldg128(cm + 256 + (ck + 2) * 16 + q * 8);
+          }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const __nv_bfloat162* sh2 = reinterpret_cast<const __nv_bfloat162*>(&shq[q]);
-          const __nv_bfloat162* sc2 = reinterpret_cast<const __nv_bfloat162*>(&scq[q]);
+        for (int q = 0; q < 2; ++q) {
+          const __nv_bfloat162* sh2 = reinterpret_cast<const __nv_bfloat162*>(&shq[ck % 3][q]);
+          const __nv_bfloat162* sc2 = reinterpret_cast<const __nv_bfloat162*>(&scq[ck % 3][q]);
           uint32_t o[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint32_t w = yreg[hb * 32 + q * 4 + k];
+            const uint32_t w = yreg[ck * 8 + q * 4 + k];
             const __nv_bfloat162 n2 = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&w), is2, nm2);
             const __nv_bfloat162 z2 = __hfma2(n2, sc2[k], sh2[k]);
             o[k] = *reinterpret_cast<const uint32_t*>(&z2);
           }
-          *reinterpret_cast<uint4*>(zbuf + (2 * hf + hb) * kKb + r * 128 + ((q ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          const int cq = (ck & 3) * 2 + q;      // 16-byte chunk of the 64-channel k-block
+          *reinterpret_cast<uint4*>(zbuf + (2 * hf + (ck >> 2)) * kKb + r * 128 + ((cq ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
       ptx::fence_proxy_async_smem();     // operand row visible to the tensor core
