@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdiffspectra_b200.so')
 
 DT_F32, DT_BF16 = 0, 1
-ACT_NONE, ACT_SILU, ACT_TANH, ACT_GELU = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_TANH, ACT_GELU, ACT_SILU_HALF, ACT_TANH_MIX = 0, 1, 2, 3, 4, 5
 MODE_FP32, MODE_BF16 = 0, 1
 SPECTRA_VERSIONS = {'uv': 0, 'ir': 1, 'raman': 2, 'allspectra': 3}
 MODEL_KINDS = {'DMT': 0, 'DMT_WO_EQ': 1}

@@ -60,6 +60,7 @@ int ds_create_model(ds_ctx** out, int device, int mode, int spectra_version, int
   if (const char* ov = getenv("DS_OVERLAP")) c->overlap = atoi(ov);
   if (const char* fv = getenv("DS_FFN")) c->ffn_variant = atoi(fv);
   if (const char* ap = getenv("DS_ATT_P1")) c->att_p1 = atoi(ap);
+  if (const char* tm = getenv("DS_TANH_MIX")) c->tanh_mix = atoi(tm);
   if (const char* lg = getenv("DS_LOOP_GRAPH")) c->loop_graph = atoi(lg);
   if (const char* ag = getenv("DS_ATT_G")) c->att_g = atoi(ag) == 4 ? 4 : 8;
   if (const char* sp = getenv("DS_SPLIT")) sscanf(sp, "%d,%d", &c->edge_cap, &c->node_cap);

@@ -120,7 +120,8 @@ constexpr int ADA_LD = 19584;                      // padded row length
 // ----------------------------------------------------------------------------- activation / dtype tags
 // ACT_SILU_HALF: the input is h = x/2 (the producing Linear was packed with 0.5 W, 0.5 b, exact in bf16):
 // SiLU(x) = x sigmoid(x) = h + h tanh(h) — one MUFU + one FFMA instead of two multiplies more.
-enum DsAct { ACT_NONE = 0, ACT_SILU = 1, ACT_TANH = 2, ACT_GELU = 3, ACT_SILU_HALF = 4 };
+// ACT_TANH_MIX (bf16 GEMM epilogues only): tanh with every second column pair on the FMA pipe (tanh_poly2) instead of MUFU.TANH.
+enum DsAct { ACT_NONE = 0, ACT_SILU = 1, ACT_TANH = 2, ACT_GELU = 3, ACT_SILU_HALF = 4, ACT_TANH_MIX = 5 };
 enum DsDType { DT_F32 = 0, DT_BF16 = 1 };
 
 typedef __nv_bfloat16 bf16;
@@ -168,7 +169,8 @@ template <bool kFast>
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
     case ACT_SILU: return act_silu<kFast>(x);
-    case ACT_TANH: return act_tanh<kFast>(x);
+    case ACT_TANH:
+    case ACT_TANH_MIX: return act_tanh<kFast>(x);       // outside the tcgen05 STORE epilogue the mix is plain tanh
     case ACT_GELU: return act_gelu(x);
     case ACT_SILU_HALF: return act_silu_half<kFast>(x);
     default: return x;
@@ -201,6 +203,29 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
       : "=f"(d.x), "=f"(d.y)
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
+}
+
+constexpr float TANH_C0 = 9.968600869e-01f, TANH_C1 = -3.149698377e-01f, TANH_C2 = 1.002266556e-01f, TANH_C3 = -2.373802848e-02f,
+                TANH_C4 = 3.820235375e-03f, TANH_C5 = -3.979499161e-04f, TANH_C6 = 2.547285476e-05f, TANH_C7 = -9.067794053e-07f,
+                TANH_C8 = 1.370746450e-08f;
+// tanh on the FMA pipe: odd minimax polynomial x P(x^2) with 9 terms on [-3.75, 3.75] (input clamped), max abs error 6.0e-4 over the
+// whole real line (MUFU.TANH: ~5e-4).  MUFU.TANH sustains ~8 results per clock per SM, a tanh epilogue over 83 M elements is
+// bound by it (37 us); 2 packed multiplies + 8 packed FMAs per PAIR run on the otherwise idle FMA pipe, so an epilogue that
+// sends every second pair here halves its MUFU time.  (The same split the FlashAttention-4 softmax uses for exp2.)
+__device__ __forceinline__ float2 tanh_poly2(float2 x) {
+  x.x = fminf(fmaxf(x.x, -3.75f), 3.75f);
+  x.y = fminf(fmaxf(x.y, -3.75f), 3.75f);
+  const float2 t = fmul2(x, x);
+  float2 p = make_float2(TANH_C8, TANH_C8);
+  p = ffma2(p, t, make_float2(TANH_C7, TANH_C7));
+  p = ffma2(p, t, make_float2(TANH_C6, TANH_C6));
+  p = ffma2(p, t, make_float2(TANH_C5, TANH_C5));
+  p = ffma2(p, t, make_float2(TANH_C4, TANH_C4));
+  p = ffma2(p, t, make_float2(TANH_C3, TANH_C3));
+  p = ffma2(p, t, make_float2(TANH_C2, TANH_C2));
+  p = ffma2(p, t, make_float2(TANH_C1, TANH_C1));
+  p = ffma2(p, t, make_float2(TANH_C0, TANH_C0));
+  return fmul2(p, x);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -24,6 +24,10 @@ struct DsContext {
   int edge_cap = 124, node_cap = 24;
   int att_g = 4;                     // DS_ATT_G: targets (= warps) per attention CTA; 4 -> 128-thread CTAs, 12 per SM: 82.1 us vs 84.4 us with 8 (finer tail); 2 targets / 64 threads measured 84.7 us
   int att_p1 = 1;                    // DS_ATT_P1: 1 = source-major pass 1 of the attention (a thread owns (source, head) and walks the targets)
+  int tanh_mix = 0;                  // DS_TANH_MIX: 1 = the tanh epilogue of lin_edge0|1 evaluates every second column pair as a polynomial on the FMA
+                                     // pipe (common.cuh tanh_poly2) instead of MUFU.TANH.  Measured on B200 ([162 305, 64] x [512, 64]^T, bf16 out):
+                                     // no activation 36.8 us, tanh 49.1 us, mix 51.2 us, SiLU 53.4 us, GELU(erf) 125 us: the epilogue is bound by
+                                     // issue slots (~3 us per instruction per element), not by MUFU, so the 7 extra instructions per pair lose
   int ffn_variant = 1;               // DS_FFN: 1 = the pre-LayerNorm row is built cooperatively while the tile is staged (55.6 us), 0 = by the row's own thread (64.0 us)
   int cta_cap = 0;                   // cap applied to the next persistent-GEMM launches (0 = all SMs)
   cudaStream_t side_stream = nullptr;

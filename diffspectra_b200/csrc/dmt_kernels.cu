@@ -1383,7 +1383,7 @@ int denoise_impl(DsContext* ctx, const PackedWeights& pw, const Plan& plan, cons
         ds_launch(k_pair_ln1<AT, kFast>, dim3(cdiv(Mp, 8)), dim3(256), 0, se, plan, w.y1, w.ada, l, reinterpret_cast<AT*>(w.ea));
         LAUNCH_CHECK(ctx);
       }
-      DS_TRY(linear(ctx, w.ea, 64, bw.w01, 64, nullptr, nullptr, 0, w.e01, E01_LD, AD, Mp, E01_LD, 64, ACT_TANH, se));
+      DS_TRY(linear(ctx, w.ea, 64, bw.w01, 64, nullptr, nullptr, 0, w.e01, E01_LD, AD, Mp, E01_LD, 64, (kFast && ctx->tanh_mix) ? ACT_TANH_MIX : ACT_TANH, se));
     }
     // ---- atom chain A: LN + modulate -> q | k | v
     ctx->cta_cap = ncap;

@@ -318,15 +318,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < BN; c += CH) {
           float f[CH];
           load_acc<CH>(t_addr + c, f);
-#pragma unroll
-          for (int i = 0; i < CH; ++i) f[i] += gb[c + i];
+          if (ep.bias) {                            // this epilogue is bound by issue slots (~3 us per instruction per element at
+#pragma unroll                                      // [162 k, 512]): no add for a Linear without bias, packed adds otherwise
+            for (int i = 0; i + 1 < CH; i += 2) {
+              const float2 v = fadd2(make_float2(f[i], f[i + 1]), *reinterpret_cast<const float2*>(gb + c + i));
+              f[i] = v.x;
+              f[i + 1] = v.y;
+            }
+          }
           if (ep.addmat && row_ok) {
             const float* ar = ep.addmat + static_cast<size_t>(row) * ep.ldadd + n0 + c;
 #pragma unroll
             for (int i = 0; i < CH; ++i)
               if (n0 + c + i < N) f[i] += __ldg(ar + i);
           }
-          if (ep.act != ACT_NONE) {
+          if (ep.act == ACT_TANH_MIX) {             // MUFU.TANH-bound epilogue: every second column pair on the FMA pipe
+#pragma unroll
+            for (int i = 0; i + 3 < CH; i += 4) {
+              const float2 pv = tanh_poly2(make_float2(f[i], f[i + 1]));
+              f[i] = pv.x;
+              f[i + 1] = pv.y;
+              f[i + 2] = act_tanh<true>(f[i + 2]);
+              f[i + 3] = act_tanh<true>(f[i + 3]);
+            }
+          } else if (ep.act != ACT_NONE) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) f[i] = apply_act<true>(f[i], ep.act);
           }

@@ -9,7 +9,7 @@ from diffspectra_b200 import _lib as L
 pytestmark = pytest.mark.gpu
 
 ACTS = {L.ACT_NONE: lambda x: x, L.ACT_SILU: torch.nn.functional.silu, L.ACT_TANH: torch.tanh,
-        L.ACT_GELU: torch.nn.functional.gelu}
+        L.ACT_GELU: torch.nn.functional.gelu, L.ACT_TANH_MIX: torch.tanh}
 
 
 @pytest.fixture(scope='module')
@@ -64,6 +64,33 @@ def test_gemm_tc_epilogue(ctx, act, out_dtype):
     tol = 2e-2 if out_dtype == torch.bfloat16 else 5e-3
     assert (buf[:, :N].float() - ref).abs().max().item() < tol
     assert (buf[:, N:] == -7.0).all()
+
+
+@pytest.mark.parametrize('scale', [0.3, 1.0, 4.0, 30.0])
+def test_gemm_tc_tanh_mix_epilogue(ctx, scale):
+    """ACT_TANH_MIX (half of the column pairs through the FMA-pipe polynomial, common.cuh tanh_poly2) against torch.tanh at
+    fp32 output: the polynomial's bound is 6.0e-4 (tests/test_host_logic.py pins the coefficients), MUFU.TANH's ~5e-4; `scale`
+    moves the pre-activations from the linear range into deep saturation (|x| >> 3.75, the clamp)."""
+    M, N, K = 1500, 512, 64
+    g = torch.Generator(device='cuda').manual_seed(11)
+    A = (torch.randn(M, K, device='cuda', generator=g) * scale).bfloat16()
+    W = (torch.randn(N, K, device='cuda', generator=g) / K ** 0.5).bfloat16()
+    pre = A.float() @ W.float().t()
+    for out_dtype, tol in ((torch.float32, 1.2e-3), (torch.bfloat16, 6e-3)):
+        out = torch.empty(M, N, device='cuda', dtype=out_dtype)
+        run_gemm(ctx, True, A, W, None, None, out, L.ACT_TANH_MIX, M, N, K)
+        err = (out.float() - torch.tanh(pre)).abs().max().item()
+        assert err < tol, (scale, out_dtype, err)
+        assert out.float().abs().max().item() <= 1.0
+        # both halves of the mix are exercised and agree with the MUFU-only epilogue to the sum of the two bounds
+        ref = torch.empty(M, N, device='cuda', dtype=out_dtype)
+        run_gemm(ctx, True, A, W, None, None, ref, L.ACT_TANH, M, N, K)
+        d = (out.float() - ref.float()).abs()
+        assert d.max().item() < (1.5e-3 if out_dtype == torch.float32 else 8e-3)
+        if out_dtype == torch.float32:
+            cols = torch.arange(N, device='cuda')
+            assert (d[:, (cols % 4) >= 2] == 0).all()          # the MUFU half is bit-identical
+            assert (d[:, (cols % 4) < 2] > 0).any()            # the polynomial half is really a different evaluation
 
 
 def test_gemm_tc_strided_views(ctx):

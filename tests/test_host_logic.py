@@ -90,3 +90,25 @@ def test_make_masks_equals_reference_loop():
     nm, em = make_masks(n, 'cpu')
     rn, re = W.make_masks(n)
     assert torch.equal(nm, rn) and torch.equal(em, re)
+
+
+def test_fma_pipe_tanh_polynomial_bound():
+    """common.cuh tanh_poly2 (the FMA-pipe half of ACT_TANH_MIX): the committed coefficients, evaluated as the kernel does
+    (fp32 Horner in x^2 on the clamped input), stay within 6.5e-4 of tanh on the whole real line and never leave [-1, 1]."""
+    import os
+    import re
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(__file__), '..', 'diffspectra_b200', 'csrc', 'common.cuh')).read()
+    c = [np.float32(re.search(r'TANH_C%d = (-?[0-9.]+e[+-][0-9]+)f' % k, src).group(1)) for k in range(9)]
+    clamp = np.float32(re.search(r'fminf\(fmaxf\(x\.x, -([0-9.]+)f\)', src).group(1))
+    x = np.concatenate([np.linspace(-12, 12, 600001), [-1e30, 1e30, 0.0]]).astype(np.float32)
+    xc = np.clip(x, -clamp, clamp)
+    t = (xc * xc).astype(np.float32)
+    p = np.full_like(t, c[8])
+    for k in range(7, -1, -1):
+        p = (p * t + c[k]).astype(np.float32)
+    p = (p * xc).astype(np.float32)
+    err = np.abs(p.astype(np.float64) - np.tanh(x.astype(np.float64)))
+    assert err.max() < 6.5e-4, err.max()
+    assert np.abs(p).max() <= 1.0
+    assert p[-1] == 0.0
