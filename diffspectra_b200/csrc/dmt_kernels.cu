@@ -629,6 +629,7 @@ __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int
   typedef typename std::conditional<kFast, __half, float>::type LT;
   __shared__ LT slog[G][MAXN][N_HEADS];
   __shared__ int srow[G][MAXN];
+  __shared__ __align__(16) uint32_t soff[G][MAXN];   // pass 2: byte offset of the pair row (source i, target) in e01; the self slot holds a neighbour's (its weight is 0)
   __shared__ float sinv[G][N_HEADS];             // 1 / softmax denominator, applied once to the accumulated messages
   // CTAs are issued largest molecule first (plan.mol_order), so the kernel's tail is made of its cheapest CTAs
   const int4 ml = __ldg(plan.mol_launch + blockIdx.x / ngrp);      // (molecule, n, noff, poff): one load, not a chain of three
@@ -645,6 +646,8 @@ __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int
   for (int idx = t; idx < gsz * n; idx += 32 * G) {
     const int jl = idx / n, i = idx - jl * n, j = j0 + jl;
     srow[jl][i] = (i == j) ? -1 : pbase + (i < j ? pair_index(n, i, j) : pair_index(n, j, i));
+    const int i2 = (i == j) ? (j == 0 ? 1 : j - 1) : i;        // any other atom of the molecule (n >= 2 wherever soff is read)
+    soff[jl][i] = n >= 2 ? static_cast<uint32_t>(pbase + (i2 < j ? pair_index(n, i2, j) : pair_index(n, j, i2))) * static_cast<uint32_t>(E01_LD * sizeof(AT)) : 0u;
   }
   __syncthreads();
   // pass 1: logits[jl][i][h] for source i -> target j
@@ -662,6 +665,12 @@ __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int
       }
       for (int jl = 0; jl < gsz; ++jl) {
         const int row = srow[jl][i];
+        {
+          // the e0 row of this thread's NEXT item goes to L1 while the current one is computed: the 14 head lanes cover its 448
+          // bytes with one 32-byte sector each (the pass is bound by the latency of its 4-byte loads, not by their count)
+          const int rown = (jl + 1 < gsz) ? srow[jl + 1][i] : (i + 2 * G < n ? srow[0][i + 2 * G] : -1);
+          if (rown >= 0 && hh < N_SUB) asm volatile("prefetch.global.L1 [%0];" ::"l"(e01 + static_cast<size_t>(rown) * E01_LD + hh * 16));
+        }
         if (row < 0) continue;
         if (hh < N_SUB) {
           const AT* er = e01 + static_cast<size_t>(row) * E01_LD + hh * 2;
@@ -775,7 +784,39 @@ __global__ void __launch_bounds__(32 * G, 48 / G) k_attention_grp(Plan plan, int
     if constexpr (sizeof(AT) == 2) {
       // four sources per iteration, all eight 16-byte loads issued before the first use; v * e1 as packed bf16
       // multiplies, weighted accumulation in fp32.  Masked slots (i == j, i >= n) read finite data with weight 0.
-      for (int i0 = 0; i0 < n; i0 += 4) {
+      // main loop: full groups of four sources, no clamps, no validity tests (the softmax wrote weight 0 into the self slot and
+      // soff points it at a neighbour's finite row), pair-row offsets of the group in ONE 16-byte shared load; the integer
+      // work of the general loop below was 40 % of this pass's instructions
+      int i0 = 0;
+      {
+        const char* eb = reinterpret_cast<const char*>(ebase);
+        const AT* vr4 = vbase;
+        const LT* sl = &slog[w][0][hh];
+        for (; i0 + 4 <= n; i0 += 4, vr4 += 4 * QKV_LD, sl += 4 * N_HEADS) {
+          const uint4 o4 = *reinterpret_cast<const uint4*>(&soff[w][i0]);
+          const uint32_t of[4] = {o4.x, o4.y, o4.z, o4.w};
+          uint4 vv[4], ee[4];
+          float al[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            vv[u] = ldg128_pinned(vr4 + u * QKV_LD);
+            ee[u] = ldg128_pinned(eb + of[u]);
+            al[u] = static_cast<float>(sl[u * N_HEADS]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
+            const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&ee[u]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 pr = bf2_to_f2(__hmul2(v2[k], e2[k]));
+              acc[2 * k] = fmaf(al[u], pr.x, acc[2 * k]);
+              acc[2 * k + 1] = fmaf(al[u], pr.y, acc[2 * k + 1]);
+            }
+          }
+        }
+      }
+      for (; i0 < n; i0 += 4) {                        // the last 1..3 sources
         uint4 vv[4], ee[4];
         float al[4];
 #pragma unroll
