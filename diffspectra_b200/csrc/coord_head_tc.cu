@@ -114,10 +114,11 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* wl_full = bars + 0;      // local: this CTA's weight halves have landed (tx)
   uint64_t* w_ready = bars + 1;      // leader: both CTAs' weights are in place (2 arrivals)
   uint64_t* x_full = bars + 2;       // leader: X tiles of both CTAs have landed (1 arrival + tx of both)
-  uint64_t* g_full = bars + 3;       // [2] both: MMA1 of the stage is complete (commit multicast)
+  uint64_t* g_full = bars + 3;       // both: MMA1 of the tile is complete (commit multicast)
+  uint64_t* g_free = bars + 4;       // leader: every build warp of both CTAs has read G out of the TMEM (16 arrivals)
   uint64_t* z_full = bars + 5;       // leader: both CTAs' operand tiles are written (2 arrivals)
-  uint64_t* acc_full = bars + 6;     // [2] both: MMA2 of the stage is complete (commit multicast)
-  uint64_t* tmem_free = bars + 8;    // [2] leader: both CTAs have drained the stage (2 arrivals)
+  uint64_t* acc_full = bars + 6;     // [2] both: MMA2 of the tile's column half is complete (commit multicast)
+  uint64_t* acc_free = bars + 8;     // [2] leader: every epilogue warp of both CTAs has drained the column half (16 arrivals)
   uint64_t* win_full = bars + 10;    // local: window landed (tx)
   uint64_t* win_free = bars + 11;    // local: window consumed (1 arrival)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
@@ -138,10 +139,11 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     ptx::mbar_init(w_ready, 2);
     ptx::mbar_init(x_full, 1);
     ptx::mbar_init(z_full, 2);
+    ptx::mbar_init(g_full, 1);
+    ptx::mbar_init(g_free, 16);                // one arrival per build warp of both CTAs
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&g_full[i], 1);
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&tmem_free[i], 16);      // one arrival per epilogue warp of both CTAs
+      ptx::mbar_init(&acc_free[i], 16);        // one arrival per epilogue warp of both CTAs
     }
     ptx::mbar_init(win_full, 1);
     ptx::mbar_init(win_free, 8);             // one arrival per build warp
@@ -173,7 +175,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t x_full_leader = ptx::mapa(ptx::smem_u32(x_full), 0);
       for (int it = 0; it < my_n; ++it) {
         const int p0 = (cid + it * ncl) * TM;
-        if (it >= 1) wait_guard(&g_full[(it - 1) & 1], ((it - 1) >> 1) & 1, 2, it);     // MMA1(it-1) has consumed the X tile
+        if (it >= 1) wait_guard(g_full, (it - 1) & 1, 2, it);                          // MMA1(it-1) has consumed the X tile
         if (rank == 0) ptx::mbar_arrive_expect_tx(x_full, 2 * 2 * kKb);                   // bytes of BOTH CTAs' tiles
         ptx::tma_load_2d_2sm(smem + OFF_X, &tmX, x_full_leader, 0, p0);
         ptx::tma_load_2d_2sm(smem + OFF_X + kKb, &tmX, x_full_leader, 64, p0);
@@ -187,45 +189,52 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // ===================== MMA issuer (leader CTA, one thread, for both CTAs) =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(256, 256);
+      // TMEM: G in columns [0, 256); the accumulator of coord_mlp.0 in two column HALVES [256, 384) and [384, 512), produced by
+      // two N = 128 MMAs per tile and drained one after the other.  G(t+1) therefore only waits for pass A(t) (g_free), not
+      // for the epilogue of tile t-1 as it did when G and the accumulator shared two 256-column stages (the build warps spent
+      // 30 % of their samples waiting for G, the epilogue warps 41 % waiting for the accumulator: profiles/r2_ncu_coord_head.md)
+      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(256, 256), idesc2 = ptx::umma_idesc_bf16(256, 128);
       wait_guard(w_ready, 0, 4, 0);
       ptx::tc_fence_after();
       const uint32_t x_addr = ptx::smem_u32(smem + OFF_X), we_addr = ptx::smem_u32(smem + OFF_WE);
       const uint32_t z_addr = ptx::smem_u32(smem + OFF_Z), wc_addr = ptx::smem_u32(smem + OFF_WC1);
-      int next1 = 0, next2 = 0;
+      int next1 = 0, next2 = 0;          // next2 counts column halves: tile = next2 >> 1, half = next2 & 1
       uint32_t idle = 0;
-      while (next2 < my_n) {
+      while (next2 < 2 * my_n) {
         bool progressed = false;
-        if (next1 < my_n && next1 <= next2 + 1) {
-          const int s = next1 & 1;
-          const bool free_ok = next1 < 2 || ptx::mbar_try_wait(&tmem_free[s], ((next1 >> 1) - 1) & 1);
+        if (next1 < my_n) {
+          const bool free_ok = next1 < 1 || ptx::mbar_try_wait(g_free, (next1 - 1) & 1);
           if (free_ok && ptx::mbar_try_wait(x_full, next1 & 1)) {
             ptx::tc_fence_after();
-            const uint32_t d = tmem_base + static_cast<uint32_t>(s * 256);
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                ptx::umma2_bf16(d, ptx::umma_smem_desc_sw128(x_addr + kb * kKb + k * 32), ptx::umma_smem_desc_sw128(we_addr + kb * kKb + k * 32),
-                                idesc, (kb | k) ? 1u : 0u);
-            ptx::umma2_commit_mc(&g_full[s], 3);
+                ptx::umma2_bf16(tmem_base, ptx::umma_smem_desc_sw128(x_addr + kb * kKb + k * 32), ptx::umma_smem_desc_sw128(we_addr + kb * kKb + k * 32),
+                                idesc1, (kb | k) ? 1u : 0u);
+            ptx::umma2_commit_mc(g_full, 3);
             ++next1;
             progressed = true;
           }
         }
-        if (next2 < next1 && ptx::mbar_try_wait(z_full, next2 & 1)) {
-          ptx::tc_fence_after();
-          const int s = next2 & 1;
-          const uint32_t d = tmem_base + static_cast<uint32_t>(s * 256);
+        {
+          const int t2 = next2 >> 1, h = next2 & 1;
+          const bool free_ok = t2 < 1 || ptx::mbar_try_wait(&acc_free[h], (t2 - 1) & 1);
+          if (t2 < next1 && free_ok && ptx::mbar_try_wait(z_full, t2 & 1)) {
+            ptx::tc_fence_after();
+            const uint32_t d = tmem_base + 256u + static_cast<uint32_t>(h * 128);
+            // column half h = rows [64 h, +64) of each CTA's half of coord_mlp.0: accumulator column c < 64 is output channel
+            // 64 h + c (leader's rows), column 64 + c is channel 128 + 64 h + c (peer's rows)
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb)
+            for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma2_bf16(d, ptx::umma_smem_desc_sw128(z_addr + kb * kKb + k * 32), ptx::umma_smem_desc_sw128(wc_addr + kb * kKb + k * 32),
-                              idesc, (kb | k) ? 1u : 0u);
-          ptx::umma2_commit_mc(&acc_full[s], 3);
-          ++next2;
-          progressed = true;
+              for (int k = 0; k < 4; ++k)
+                ptx::umma2_bf16(d, ptx::umma_smem_desc_sw128(z_addr + kb * kKb + k * 32),
+                                ptx::umma_smem_desc_sw128(wc_addr + kb * kKb + h * (64 * 128) + k * 32), idesc2, (kb | k) ? 1u : 0u);
+            ptx::umma2_commit_mc(&acc_full[h], 3);
+            ++next2;
+            progressed = true;
+          }
         }
         if (progressed) idle = 0;
         else if (++idle > (1u << 24)) {
@@ -245,7 +254,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
     const int hf = warp >> 2, wq = warp & 3, r = wq * 32 + lane;     // r = row inside the tile = TMEM lane; hf = channel half
     const int cb = hf * 128;
-    const uint32_t z_full_leader = ptx::mapa(ptx::smem_u32(z_full), 0);
+    const uint32_t z_full_leader = ptx::mapa(ptx::smem_u32(z_full), 0), g_free_leader = ptx::mapa(ptx::smem_u32(g_free), 0);
     float2* sstat = reinterpret_cast<float2*>(smem + OFF_STAT);      // [2][128] (sum, sum of squares) of each channel half
     uint8_t* zbuf = smem + OFF_Z;
     const uint8_t* win = smem + OFF_WIN;
@@ -266,7 +275,6 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int it = 0; it < my_n; ++it) {
       DS_STAMP(0);
       uint32_t yreg[64];          // the thread's 128 channels of y, packed bf16 pairs
-      const int s = it & 1;
       const int2 rows = rows_n;
       const int mol = mol_n, a_lo = alo_n;
       if (it + 1 < my_n) load_idx(it + 1, rows_n, mol_n, alo_n);
@@ -277,7 +285,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const bf16* vrow = a.ab + static_cast<size_t>(rows.y) * 512 + (rank ? 0 : 256) + cb;
       const int wr = rows.y - a_lo;
       const bool in_win = wr >= 0 && wr < kWinRows;
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(s * 256 + cb);
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(cb);
       if (it == 0) {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(urow));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(urow + 64));
@@ -287,7 +295,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 64));
       asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 256));
       asm volatile("prefetch.global.L1 [%0];" ::"l"(cm + 320));
-      wait_guard(&g_full[s], (it >> 1) & 1, 5, it);
+      wait_guard(g_full, it & 1, 5, it);
       ptx::tc_fence_after();
       DS_STAMP(1);
       wait_guard(win_full, it & 1, 6, it);
@@ -335,9 +343,12 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         asm volatile("prefetch.global.L1 [%0];" ::"l"(un));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(un + 64));
       }
-      ptx::tc_fence_before();            // this thread's reads of G precede the MMA2 that overwrites those columns
+      ptx::tc_fence_before();            // this thread's reads of G precede the MMA1 of the next tile, which overwrites those columns
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(win_free);                 // this warp is done with the window
+      if (lane == 0) {
+        ptx::mbar_arrive_remote(g_free_leader);                  // this warp has G in registers
+        ptx::mbar_arrive(win_free);                              // and is done with the window
+      }
       // the two threads of a row sit in warps w and w ^ 4: a 64-thread named barrier per warp pair, not one over all 8 warps
       asm volatile("bar.sync %0, 64;" ::"r"(4 + wq) : "memory");
       const float2 mine = sstat[hf * 128 + r], other = sstat[(hf ^ 1) * 128 + r];
@@ -345,7 +356,7 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const float is = rsqrtf(fmaxf((mine.y + other.y) * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-6f);
       DS_STAMP(3);
       // the operand buffer is free once MMA2 of the previous tile has completed
-      if (it >= 1) wait_guard(&acc_full[s ^ 1], ((it - 1) >> 1) & 1, 7, it);
+      if (it >= 1) wait_guard(&acc_full[1], (it - 1) & 1, 7, it);      // the second column half is issued last
       DS_STAMP(4);
       // ---- pass B: normalise + modulate from the registers -> bf16 -> SWIZZLE_128B K-major operand row
       // z = (y rstd - mean rstd) (1 + scale) + shift as TWO packed bf16 fmas per channel pair (fp32 inside each, one rounding
@@ -400,11 +411,10 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // special-function unit fed while the build warps use the other pipes.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     const int hf = (warp - 8) >> 2, wq = warp & 3, r = wq * 32 + lane;
-    const int cb = hf * 128;
-    const float4* stab = reinterpret_cast<const float4*>(smem + OFF_TAB) + cb;
-    float4* spart = reinterpret_cast<float4*>(smem + OFF_PART);      // [128] partial sums of the upper channel half
+    const float4* stab0 = reinterpret_cast<const float4*>(smem + OFF_TAB);
+    float4* spart = reinterpret_cast<float4*>(smem + OFF_PART);      // [128] partial sums of the second thread of a row
+    const uint32_t acc_free_leader = ptx::mapa(ptx::smem_u32(acc_free), 0);
     for (int it = 0; it < my_n; ++it) {
-      const int s = it & 1;
       const int p0 = (cid + it * ncl) * TM;
       const int p = p0 + r;
       const bool ok = p < a.Mp;
@@ -414,37 +424,43 @@ coord_head_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int nat = __ldg(a.n_atoms + mol), pb = __ldg(a.poff + mol);
       const uint8_t fl = __ldg(a.pflags + pc);
       const size_t d_out = static_cast<size_t>(2) * pb + (rank ? static_cast<size_t>(aj) * (nat - 1) + ai : static_cast<size_t>(ai) * (nat - 1) + (aj - 1));
-      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(s * 256 + cb);
-      wait_guard(&acc_full[s], (it >> 1) & 1, 8, it);
-      ptx::tc_fence_after();
       float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0, q4 = q0, q5 = q0;     // two chains per output
-      uint32_t eacc[2][16];
-      ptx::tmem_ld16_nowait(t_acc, eacc[0]);
-#pragma unroll 4
-      for (int c = 0; c < 128; c += 16) {
-        uint32_t (&acc)[16] = eacc[(c >> 4) & 1];
-        ptx::tmem_wait_ld16(acc);
-        if (c + 16 < 128) ptx::tmem_ld16_nowait(t_acc + c + 16, eacc[((c >> 4) + 1) & 1]);
+      // the accumulator arrives as two column halves; of each, this thread takes columns [64 hf, +64) = output channels
+      // 128 hf + 64 ch + [0, 64) (the MMA issuer's comment has the column <-> channel map of an N = 128 pair MMA)
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(256 + ch * 128 + hf * 64);
+        const float4* stab = stab0 + hf * 128 + ch * 64;
+        wait_guard(&acc_full[ch], it & 1, 8, it);
+        ptx::tc_fence_after();
+        uint32_t eacc[2][16];
+        ptx::tmem_ld16_nowait(t_acc, eacc[0]);
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float4 wa = stab[c + i], wb = stab[c + i + 1];
-          const float2 h = fadd2(make_float2(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1])), make_float2(wb.z, wb.w));
-          const float2 v = ffma2(h, make_float2(act_tanh<true>(h.x), act_tanh<true>(h.y)), h);   // SiLU(2h) = h + h tanh(h)
-          if (i & 2) {
-            q3 = ffma2(v, make_float2(wa.x, wa.y), q3);
-            q4 = ffma2(v, make_float2(wa.z, wa.w), q4);
-            q5 = ffma2(v, make_float2(wb.x, wb.y), q5);
-          } else {
-            q0 = ffma2(v, make_float2(wa.x, wa.y), q0);
-            q1 = ffma2(v, make_float2(wa.z, wa.w), q1);
-            q2 = ffma2(v, make_float2(wb.x, wb.y), q2);
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t (&acc)[16] = eacc[(c >> 4) & 1];
+          ptx::tmem_wait_ld16(acc);
+          if (c + 16 < 64) ptx::tmem_ld16_nowait(t_acc + c + 16, eacc[((c >> 4) + 1) & 1]);
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float4 wa = stab[c + i], wb = stab[c + i + 1];
+            const float2 h = fadd2(make_float2(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1])), make_float2(wb.z, wb.w));
+            const float2 v = ffma2(h, make_float2(act_tanh<true>(h.x), act_tanh<true>(h.y)), h);   // SiLU(2h) = h + h tanh(h)
+            if (i & 2) {
+              q3 = ffma2(v, make_float2(wa.x, wa.y), q3);
+              q4 = ffma2(v, make_float2(wa.z, wa.w), q4);
+              q5 = ffma2(v, make_float2(wb.x, wb.y), q5);
+            } else {
+              q0 = ffma2(v, make_float2(wa.x, wa.y), q0);
+              q1 = ffma2(v, make_float2(wa.z, wa.w), q1);
+              q2 = ffma2(v, make_float2(wb.x, wb.y), q2);
+            }
           }
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_remote(acc_free_leader + ch * 8);        // this warp's columns of the half are drained
       }
       float s0 = (q0.x + q0.y) + (q3.x + q3.y), s1 = (q1.x + q1.y) + (q4.x + q4.y), s2 = (q2.x + q2.y) + (q5.x + q5.y);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(&tmem_free[s]), 0));      // this warp's columns are drained
       if (hf == 1) spart[r] = make_float4(s0, s1, s2, 0.f);
       asm volatile("bar.sync %0, 64;" ::"r"(8 + wq) : "memory");       // warps w and w + 4 hold the two halves of a row
       if (hf == 0 && ok) {
