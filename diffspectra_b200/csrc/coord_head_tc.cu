@@ -12,23 +12,29 @@
 // LayerNorm'd operand Z in shared memory, only X (41 MB), the L2-resident per-atom table `ab` and the 4-byte results
 // cross HBM.
 //
-// The CTA pair works on ONE tile of 128 pairs at a time; CTA rank 0 owns the forward edges (i -> j) of those pairs, rank 1
-// the reverse edges (j -> i).  Both MMAs are cta_group::2 instructions of M = 256 (128 rows per CTA, rows of the two CTAs
-// = the two directions), N = 256, issued by one thread of the leader CTA: each CTA keeps only HALF of the two weight
-// matrices resident (coord_mlp.0: 64 KB, input_lin[e | dist]: 32 KB), which is what makes room for the 64 KB operand
-// tile, and every weight byte read from shared memory feeds 256 rows.
+// The CTA pair works on tiles of 128 pairs; CTA rank 0 owns the forward edges (i -> j) of those pairs, rank 1 the reverse
+// edges (j -> i).  All MMAs are cta_group::2 instructions of M = 256 (128 rows per CTA, rows of the two CTAs = the two
+// directions) issued by one thread of the leader CTA: each CTA keeps only HALF of the two weight matrices resident
+// (coord_mlp.0: 64 KB, input_lin[e | dist]: 32 KB), which is what makes room for the 64 KB operand tile, and every weight
+// byte read from shared memory feeds 256 rows.
 //
-// Per CTA: 10 warps.
-//   warps 0-7         compute: TWO threads per directed edge (= TMEM lane; warps w and w + 4 share a lane quadrant and split
-//                     the 256 channels).  Software pipeline over the tiles: pass A(t) (y = G + A + B, LayerNorm statistics; y
-//                     stays in registers as packed bf16) -> epilogue(t-1) (SiLU, 3 dot products, tanh, adjacency mean -> w[d])
-//                     -> pass B(t) (normalise + modulate -> operand tile Z in shared memory, SWIZZLE_128B) -> MMA2(t) overwrites
-//                     G's TMEM columns.  Two TMEM stages of 256 columns: MMA1(t+1) runs under pass B(t), MMA2(t) under pass A(t+1).
-//   warp 8            loader: weights once; per tile the X tile (TMA, counted on the leader's barrier) and the "window":
-//                     the lane-varying halves of the `ab` rows of up to 48 consecutive atoms starting at the tile's first
-//                     atom (TMA, swizzled, so that 32 lanes reading 32 different atoms do not bank-conflict); atoms beyond
-//                     the window (runs of tiny molecules) are read from global memory.
-//   warp 9            TMEM owner; in the leader CTA also the MMA issuer for both CTAs.
+// TMEM (512 columns per CTA): G of the current tile in [0, 256) (MMA1, N = 256); the accumulator of coord_mlp.0 as two column
+// HALVES [256, 384) and [384, 512) (two N = 128 MMA2s per tile), drained one after the other.  G(t+1) only waits for pass A(t)
+// of both CTAs (g_free), the halves of MMA2(t) for the epilogue of the same half of tile t-1 (acc_free), the operand tile Z
+// for MMA2(t-1) (acc_full[1]): build and epilogue run one tile apart without meeting in the TMEM.
+//
+// Per CTA: 20 warps (640 threads; the register file is re-divided with setmaxnreg: 144 / 72 / 40 registers per thread).
+//   warps 0-7    build: TWO threads per directed edge (= TMEM lane; warps w and w + 4 share a lane quadrant and split the 256
+//                channels).  Pass A(t): y = G + A + B, LayerNorm statistics, y kept in REGISTERS as packed bf16; pass B(t):
+//                normalise + modulate -> operand tile Z in shared memory (SWIZZLE_128B) -> MMA2(t).
+//   warps 8-15   epilogue: two threads per directed edge, 64 columns of each accumulator half: SiLU, the three dot products
+//                of coord_mlp.2, tanh, adjacency mean -> w[d].  MUFU.TANH-bound; runs next to the build of tile t+1.
+//   warp 16      loader: weights once; per tile the X tile (TMA, counted on the leader's barrier) and the "window": the
+//                lane-varying halves of the `ab` rows of up to 48 consecutive atoms starting at the tile's first atom (TMA,
+//                swizzled, so that 32 lanes reading 32 different atoms do not bank-conflict); atoms beyond the window (runs
+//                of tiny molecules) are read from global memory.
+//   warp 17      TMEM owner; in the leader CTA also the MMA issuer for both CTAs.
+//   warps 18-19  idle: their registers go to the build warps.
 // Every mbarrier wait is bounded: a protocol error traps with a message instead of hanging the GPU.
 #include <stdlib.h>
 #include <string.h>
@@ -88,17 +94,6 @@ __device__ __forceinline__ uint4 ldg128(const void* p) {
   uint4 v;
   asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
-}
-__device__ __forceinline__ float4 ldg128f(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
-  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
-  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
-  v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
-  v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
