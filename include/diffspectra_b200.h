@@ -142,9 +142,7 @@ int ds_molecule_records(ds_ctx* ctx, const void* plan, int B, int N, int Mn, int
                         const float* edge_mean, int rec_n, void* records, size_t records_bytes, void* stream);
 
 /* Test hook: out[M,N] = act(A[M,K] W[N,K]^T + bias + addmat).  use_tensor_cores=1 -> the tcgen05/TMA kernel
- * (bf16 A/W), 0 -> the CUDA-core kernel.  dtype 0 = f32, 1 = bf16; act 0 none, 1 SiLU, 2 tanh, 3 GELU(erf), 4 SiLU(2x) (the
- * producing Linear stored halved), 5 tanh with every second column pair evaluated as a polynomial on the FMA pipe (max abs
- * error 6.0e-4; tcgen05 kernel only, plain tanh elsewhere). */
+ * (bf16 A/W), 0 -> the CUDA-core kernel.  dtype 0 = f32, 1 = bf16; act 0 none, 1 SiLU, 2 tanh, 3 GELU(erf). */
 int ds_gemm(ds_ctx* ctx, int use_tensor_cores, const void* A, int lda, const void* W, int ldw, const float* bias,
             const float* addmat, int ldadd, void* out, int ldo, int M, int N, int K, int in_dtype, int out_dtype,
             int act, void* stream);
